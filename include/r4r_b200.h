@@ -1,0 +1,126 @@
+/* r4r_b200.h -- C ABI of the B200-native rating-prediction training hot path.
+ *
+ * Drop-in boundary for noveens/reviews4rec's training path (main.py + loss.py driving
+ * pytorch_models/).  The reference is pure Python/PyTorch and has no FFI of its own; every entry
+ * point below therefore replaces a *library op dispatched by PyTorch on the reference's behalf*
+ * and cites the reference call site (file:line under /root/reference) it stands in for.
+ *
+ * Conventions
+ *   - plain C: device pointers + sizes, no torch types.  All pointers are DEVICE pointers unless
+ *     the parameter name ends in _host.  `stream` is a cudaStream_t passed as void* (NULL = legacy
+ *     default stream).  Nothing allocates device memory; callers own every buffer.
+ *   - every function returns 0 on success, a negative R4R_E* code on argument errors, or a positive
+ *     cudaError_t.  r4r_last_error() returns a thread-local message for the last failure.  The
+ *     reference validates nothing (SURVEY.md 8b "error conventions"); the Python host layer turns
+ *     non-zero returns into RuntimeError.
+ *   - fp32 everywhere except the private fp16/bf16 "shadow" word table read by the tensor-core
+ *     conv; ids are int64 exactly as the reference's LongTensors (data_fast.py:102-108).
+ *   - launches are asynchronous on `stream`; no host synchronisation happens inside the library.
+ */
+#ifndef R4R_B200_H
+#define R4R_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define R4R_ABI_VERSION 1
+
+#define R4R_EINVAL   (-1)   /* bad argument (null pointer, size out of supported range)          */
+#define R4R_EUNSUP   (-2)   /* shape outside what the sm_100a kernels were built for             */
+#define R4R_ENODEV   (-3)   /* no sm_100 device                                                  */
+
+#define R4R_DT_F16   0
+#define R4R_DT_BF16  1
+
+int         r4r_abi_version(void);
+const char* r4r_last_error(void);
+/* name[64], returns sm count / compute capability of the current device. */
+int         r4r_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* smem_optin_bytes);
+
+/* ---- a4: word-embedding gather --------------------------------------------------------------
+ * out[i,:] = table[idx[i],:]            replaces nn.Embedding.forward / aten::index_select at
+ * DeepCoNN.py:53-54, NARRE.py:95-96, TransNet.py:52-53,100-102.  Bit-exact copy. */
+int r4r_word_gather_f32(const float* table, int64_t V, int E, const int64_t* idx, int64_t n,
+                        float* out, void* stream);
+
+/* Private reduced-precision copy of the frozen word table (SURVEY.md finding 2):
+ * shadow[v, 0:E] = cvt(table[v,:]), shadow[v, E:Epad] = 0.  Epad % 8 == 0, row stride = Epad. */
+int r4r_shadow_build(const float* table, int64_t V, int E, void* shadow, int Epad, int dtype,
+                     void* stream);
+
+/* ---- a5: TextCNN conv + ReLU + global max-pool, fused with the gather ------------------------
+ * For doc n (row of idx[N,T]) and filter f:
+ *   y[p] = sum_{j<3} sum_e Xpad[p+j, e] * W[f,0,j,e],  Xpad = 2 zero rows | table[idx[n,:]] | 2 zero rows
+ *   pooled[n,f] = relu(max_p y[p] + bias[f]),  argmax[n,f] = first p attaining the max, p in [0,T+2)
+ * replaces F.conv2d(padding=(2,0)) + F.relu + F.max_pool1d at common_pytorch_models.py:26-31
+ * (Conv2d built at :14-17).  window size is the reference default 3.
+ * r4r_conv_pool_simt: exact fp32 FMA arithmetic (parity mode).  keys_ws: N*F uint64 workspace. */
+int r4r_conv_pool_simt(const float* table, int64_t V, int E, const int64_t* idx, int64_t N, int T,
+                       const float* conv_w, const float* conv_b, int F,
+                       float* pooled, int32_t* argmax, uint64_t* keys_ws, void* stream);
+
+/* Tensor-core path (tcgen05.mma kind::f16, fp32 accumulate in TMEM).
+ * r4r_conv_pack_weights: conv_w [F,1,3,E] fp32 -> operand image `wpack` in the kernel's smem layout
+ * (r4r_conv_wpack_bytes(E,F) bytes).  Re-run after every optimizer step that changes conv_w. */
+int64_t r4r_conv_wpack_bytes(int E, int F);
+int r4r_conv_pack_weights(const float* conv_w, int E, int F, void* wpack, int dtype, void* stream);
+int r4r_conv_pool_tc(const void* shadow, int64_t V, int Epad, int E, int dtype,
+                     const int64_t* idx, int64_t N, int T,
+                     const void* wpack, const float* conv_b, int F,
+                     float* pooled, int32_t* argmax, void* stream);
+
+/* ---- a11: conv weight gradient through relu+max-pool (SURVEY.md finding 4) --------------------
+ * dW[f,0,j,:] += sum_n gy[n,f] * Xpad[n, argmax[n,f]+j, :],  db[f] += sum_n gy[n,f]
+ * with gy = gpooled * (pooled > 0).  Replaces autograd's convolution_backward + relu/max-pool
+ * backward for TextCNN (main.py:59).  dW/db are ACCUMULATED into (zero them first). */
+int r4r_conv_wgrad_argmax(const float* table, int64_t V, int E, const int64_t* idx, int64_t N, int T,
+                          const int32_t* argmax, const float* pooled, const float* gpooled, int F,
+                          float* dW, float* db, void* stream);
+
+/* ---- small dense layers of the heads ----------------------------------------------------------
+ * y[n,o] = sum_i x[n,i] W[o,i] + b[o]   (nn.Linear: TextCNN.fc common_pytorch_models.py:19,37;
+ * DeepCoNN.final DeepCoNN.py:21-26; NARRE scorers NARRE.py:24-43; TransNet project TransNet.py:17-21) */
+int r4r_linear_fwd(const float* x, const float* W, const float* b, int64_t n, int in_f, int out_f,
+                   float* y, void* stream);
+/* dx = gy W (may be NULL); dW += gy^T x; db += sum_n gy  (dW/db accumulated, may be NULL) */
+int r4r_linear_bwd(const float* x, const float* W, const float* gy, int64_t n, int in_f, int out_f,
+                   float* dx, float* dW, float* db, void* stream);
+
+/* ---- a6: TorchFM second-order interaction (common_pytorch_models.py:49-57) --------------------
+ * out[n] = 0.5*(sum_k (xV)_k^2 - sum_k (x^2 V^2)_k) + x.w + b        x [n,nf], V [nf,k], w [nf] */
+int r4r_fm_fwd(const float* x, const float* V, const float* w, const float* b, int64_t n, int nf, int k,
+               float* out, void* stream);
+int r4r_fm_bwd(const float* x, const float* V, const float* w, const float* gout, int64_t n, int nf, int k,
+               float* dx, float* dV, float* dw, float* db, void* stream);
+
+/* ---- a3: MSE (loss.py:7-11) -------------------------------------------------------------------
+ * se[n] = (out[n]-y[n])^2 ; *sum_se += sum_n se[n] (device scalar, accumulated; may be NULL) */
+int r4r_mse_fwd(const float* out, const float* y, int64_t n, float* se, float* sum_se, void* stream);
+/* gout[n] = gse[n] * 2*(out[n]-y[n])   (gse = upstream grad of se, e.g. 1/B for the mean) */
+int r4r_mse_bwd(const float* out, const float* y, const float* gse, int64_t n, float* gout, void* stream);
+
+/* ---- a7-a10: id-embedding / bias row gathers and their gradient scatter ----------------------
+ * out[i,:] = table[ids[i],:]   replaces nn.Embedding / Tensor.gather at MF.py:45-46,52-53,
+ * NARRE.py:87-88,110-116, TransNet.py:108-109, DeepCoNN.py:70-71  (L = 1 for the bias vectors) */
+int r4r_rows_gather(const float* table, int64_t R, int L, const int64_t* ids, int64_t n, float* out,
+                    void* stream);
+/* gtable[ids[i],:] += gout[i,:]  (dense gradient as autograd's embedding_dense_backward produces;
+ * duplicates are combined inside each warp before one atomic per distinct row) */
+int r4r_rows_scatter_add(const float* gout, const int64_t* ids, int64_t n, int L, float* gtable, int64_t R,
+                         void* stream);
+
+/* ---- a12: fused dense Adam (torch.optim.Adam as configured at main.py:94-96) -----------------
+ * For each tensor t < nt:  g = grad + wd*p; m,v moments; p -= lr/bc1 * m/(sqrt(v)/sqrt(bc2)+eps).
+ * Arrays of DEVICE pointers are passed from the HOST (p_host[t] etc.).  `step` is the 1-based step
+ * count; if step_dev != NULL the kernel reads the count from device memory instead (CUDA graphs). */
+int r4r_adam_step(int nt, float* const* p_host, const float* const* g_host, float* const* m_host,
+                  float* const* v_host, const int64_t* numel_host, int step, const int32_t* step_dev,
+                  float lr, float beta1, float beta2, float eps, float weight_decay, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* R4R_B200_H */

@@ -1,0 +1,134 @@
+// wgrad.cu -- K4: conv weight/bias gradient through ReLU + global max-pool.
+//
+// Only the arg-max window of each (doc, filter) receives gradient (SURVEY.md finding 4), so the
+// reference's dense convolution_backward GEMM (36% of its CPU step) collapses to a re-gather of
+// <= 3 rows per (doc, filter):
+//     dW[f,0,j,:] += sum_n gy[n,f] * Xpad[n, argmax[n,f] + j, :]      gy = gpooled * [pooled > 0]
+//     db[f]       += sum_n gy[n,f]
+// Grid = F x S: CTA (f, s) owns filter f and the s-th slice of documents; each thread keeps its
+// float4 slices of the 3xE window in registers across the slice, then commits them with one
+// atomicAdd per element.  The gathered rows come from the fp32 word table, which is L2-resident at
+// the reference's vocabulary (50,001 x 300 x 4 B = 60 MB < 126 MB L2), so this kernel is bound by
+// L2 gather bandwidth, not HBM: N*F*3 row reads of 4E bytes.
+#include "common.cuh"
+
+namespace {
+constexpr int THREADS = 256;
+constexpr int MAXV = 3;       // float4 accumulators per thread: 3*E/4 <= MAXV*THREADS  -> E <= 1024
+
+template <int NV>
+__global__ void __launch_bounds__(THREADS) conv_wgrad_kernel(
+    const float* __restrict__ table, int64_t V, int E, const int64_t* __restrict__ idx, int64_t N, int T,
+    const int32_t* __restrict__ argmax, const float* __restrict__ pooled, const float* __restrict__ gpooled,
+    int F, float* __restrict__ dW, float* __restrict__ db) {
+  const int f = blockIdx.x;
+  const int64_t per = (N + gridDim.y - 1) / gridDim.y;
+  const int64_t n0 = (int64_t)blockIdx.y * per;
+  const int64_t n1 = (n0 + per < N) ? n0 + per : N;
+  const int e4 = E >> 2;
+  const int nvec = 3 * e4;
+  const int tid = threadIdx.x;
+
+  float4 acc[NV];
+  int vj[NV], vc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int q = tid + v * THREADS;
+    vj[v] = q < nvec ? q / e4 : -1;
+    vc[v] = q < nvec ? q % e4 : 0;
+  }
+  float bsum = 0.0f;
+
+  for (int64_t n = n0; n < n1; ++n) {
+    const float p = __ldg(pooled + n * F + f);
+    const float g = __ldg(gpooled + n * F + f);
+    if (!(p > 0.0f) || g == 0.0f) continue;            // CTA-uniform: dead ReLU or zero upstream grad
+    const int a = __ldg(argmax + n * F + f);
+    bsum += g;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      if (vj[v] < 0) continue;
+      int pos = a + vj[v] - 2;                          // document row feeding window row j
+      if (pos < 0 || pos >= T) continue;                // zero padding row
+      int64_t tok = __ldg(idx + n * (int64_t)T + pos);
+      float4 x = __ldg(reinterpret_cast<const float4*>(table + tok * (int64_t)E) + vc[v]);
+      acc[v].x = fmaf(g, x.x, acc[v].x);
+      acc[v].y = fmaf(g, x.y, acc[v].y);
+      acc[v].z = fmaf(g, x.z, acc[v].z);
+      acc[v].w = fmaf(g, x.w, acc[v].w);
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    if (vj[v] < 0) continue;
+    float* dst = dW + ((int64_t)f * 3 + vj[v]) * E + vc[v] * 4;
+    atomicAdd(dst + 0, acc[v].x);
+    atomicAdd(dst + 1, acc[v].y);
+    atomicAdd(dst + 2, acc[v].z);
+    atomicAdd(dst + 3, acc[v].w);
+  }
+  if (tid == 0 && bsum != 0.0f) atomicAdd(db + f, bsum);
+}
+
+// scalar fallback for E % 4 != 0 (tiny test shapes): one thread per (j, e) element, strided
+__global__ void __launch_bounds__(THREADS) conv_wgrad_scalar_kernel(
+    const float* __restrict__ table, int64_t V, int E, const int64_t* __restrict__ idx, int64_t N, int T,
+    const int32_t* __restrict__ argmax, const float* __restrict__ pooled, const float* __restrict__ gpooled,
+    int F, float* __restrict__ dW, float* __restrict__ db) {
+  const int f = blockIdx.x;
+  const int64_t per = (N + gridDim.y - 1) / gridDim.y;
+  const int64_t n0 = (int64_t)blockIdx.y * per;
+  const int64_t n1 = (n0 + per < N) ? n0 + per : N;
+  for (int q = threadIdx.x; q < 3 * E; q += THREADS) {
+    int j = q / E, e = q % E;
+    float acc = 0.0f;
+    for (int64_t n = n0; n < n1; ++n) {
+      const float p = __ldg(pooled + n * F + f);
+      const float g = __ldg(gpooled + n * F + f);
+      if (!(p > 0.0f) || g == 0.0f) continue;
+      int pos = __ldg(argmax + n * F + f) + j - 2;
+      if (pos < 0 || pos >= T) continue;
+      int64_t tok = __ldg(idx + n * (int64_t)T + pos);
+      acc = fmaf(g, __ldg(table + tok * (int64_t)E + e), acc);
+    }
+    atomicAdd(dW + ((int64_t)f * 3 + j) * E + e, acc);
+  }
+  if (threadIdx.x == 0) {
+    float bsum = 0.0f;
+    for (int64_t n = n0; n < n1; ++n) {
+      const float p = __ldg(pooled + n * F + f);
+      if (p > 0.0f) bsum += __ldg(gpooled + n * F + f);
+    }
+    if (bsum != 0.0f) atomicAdd(db + f, bsum);
+  }
+}
+}  // namespace
+
+extern "C" int r4r_conv_wgrad_argmax(const float* table, int64_t V, int E, const int64_t* idx, int64_t N, int T,
+                                     const int32_t* argmax, const float* pooled, const float* gpooled, int F,
+                                     float* dW, float* db, void* stream) {
+  R4R_REQUIRE(table && idx && argmax && pooled && gpooled && dW && db, R4R_EINVAL, "conv_wgrad: null pointer");
+  R4R_REQUIRE(V > 0 && E > 0 && T > 0 && N >= 0 && F > 0, R4R_EINVAL, "conv_wgrad: bad sizes");
+  if (N == 0) return 0;
+  cudaStream_t s = as_stream(stream);
+  // document slices: enough CTAs for >= 4 waves of 148 SMs x 8 resident CTAs, >= 16 docs each
+  int64_t want = (148 * 8 * 4 + F - 1) / F;
+  int64_t S = N / 16;
+  if (S > want) S = want;
+  if (S < 1) S = 1;
+  if (S > 65535) S = 65535;
+  dim3 grid((unsigned)F, (unsigned)S);
+  const bool vec = (E % 4 == 0) && (reinterpret_cast<uintptr_t>(table) % 16 == 0);
+  if (!vec) {
+    conv_wgrad_scalar_kernel<<<grid, THREADS, 0, s>>>(table, V, E, idx, N, T, argmax, pooled, gpooled, F, dW, db);
+  } else {
+    int nvec = 3 * (E / 4);
+    R4R_REQUIRE(nvec <= MAXV * THREADS, R4R_EUNSUP, "conv_wgrad: E=%d too wide (max %d)", E, MAXV * THREADS * 4 / 3);
+    if (nvec <= THREADS)          conv_wgrad_kernel<1><<<grid, THREADS, 0, s>>>(table, V, E, idx, N, T, argmax, pooled, gpooled, F, dW, db);
+    else if (nvec <= 2 * THREADS) conv_wgrad_kernel<2><<<grid, THREADS, 0, s>>>(table, V, E, idx, N, T, argmax, pooled, gpooled, F, dW, db);
+    else                          conv_wgrad_kernel<3><<<grid, THREADS, 0, s>>>(table, V, E, idx, N, T, argmax, pooled, gpooled, F, dW, db);
+  }
+  R4R_CHECK_LAUNCH("conv_wgrad");
+  return 0;
+}

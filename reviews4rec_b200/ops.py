@@ -1,0 +1,269 @@
+"""Autograd-visible operators of the hot path; each one is a thin host wrapper over one or two
+C-ABI calls (include/r4r_b200.h).  Tensors only provide device memory and the current stream.
+
+There is deliberately no CPU implementation: a non-CUDA tensor raises RuntimeError.
+"""
+import ctypes
+import os
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import call
+
+NUM_FILTERS = 100          # common_pytorch_models.py:11
+_MODES = ("exact", "f16", "bf16")
+_conv_mode = os.environ.get("R4R_CONV_MODE", "f16")
+
+
+def set_conv_mode(mode: str) -> None:
+    """'exact' = fp32 CUDA-core kernel (strict parity); 'f16' / 'bf16' = tcgen05 tensor-core kernel
+    reading a private half-precision shadow of the frozen word table (fp32 accumulation)."""
+    global _conv_mode
+    if mode not in _MODES:
+        raise ValueError("conv mode must be one of %s" % (_MODES,))
+    _conv_mode = mode
+
+
+def get_conv_mode() -> str:
+    return _conv_mode
+
+
+def _p(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("reviews4rec_b200 kernels run on CUDA tensors only (got a %s tensor); "
+                               "there is no CPU fallback" % t.device)
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError("expected float32, got %s" % t.dtype)
+    return t.contiguous()
+
+
+def _i64c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.int64:
+        raise TypeError("ids must be int64 (LongTensor) as in the reference, got %s" % t.dtype)
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------------------------ gather
+def word_gather(table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """nn.Embedding forward on the frozen word table (DeepCoNN.py:53-54).  Bit-exact row copies."""
+    _need_cuda(table, idx)
+    table, idx = _f32c(table), _i64c(idx)
+    out = torch.empty(*idx.shape, table.shape[1], device=table.device, dtype=torch.float32)
+    call("r4r_word_gather_f32", _p(table), table.shape[0], table.shape[1], _p(idx), idx.numel(), _p(out), _stream())
+    return out
+
+
+class ShadowTable:
+    """fp16/bf16 padded copy of a frozen fp32 word table, rebuilt only when the table changes
+    (xavier_init / load_state_dict bump ``_version``)."""
+
+    def __init__(self):
+        self._key = None
+        self.tensor = None
+        self.epad = 0
+
+    def get(self, table: torch.Tensor, mode: str) -> torch.Tensor:
+        key = (table.data_ptr(), table._version, tuple(table.shape), mode)
+        if key != self._key:
+            V, E = table.shape
+            self.epad = ((E + 63) // 64) * 64                     # 128-byte aligned rows
+            dt = torch.float16 if mode == "f16" else torch.bfloat16
+            self.tensor = torch.empty(V, self.epad, device=table.device, dtype=dt)
+            call("r4r_shadow_build", _p(table), V, E, _p(self.tensor), self.epad,
+                 _lib.R4R_DT_F16 if mode == "f16" else _lib.R4R_DT_BF16, _stream())
+            self._key = key
+        return self.tensor
+
+
+# ------------------------------------------------------------------------------------ conv + pool
+def conv_pool_forward(idx: torch.Tensor, table: torch.Tensor, conv_w: torch.Tensor, conv_b: torch.Tensor,
+                      mode: str, shadow: Optional[ShadowTable] = None):
+    """Fused gather -> conv(3xE, pad 2) -> relu -> global max-pool.  Returns (pooled [N,F], argmax [N,F])."""
+    _need_cuda(idx, table, conv_w, conv_b)
+    idx, table, conv_w, conv_b = _i64c(idx), _f32c(table), _f32c(conv_w), _f32c(conv_b)
+    N, T = idx.shape
+    V, E = table.shape
+    F = conv_w.shape[0]
+    if tuple(conv_w.shape) != (F, 1, 3, E):
+        raise RuntimeError("conv weight must be [F,1,3,%d] (window size 3), got %s" % (E, tuple(conv_w.shape)))
+    pooled = torch.empty(N, F, device=table.device, dtype=torch.float32)
+    argmax = torch.empty(N, F, device=table.device, dtype=torch.int32)
+    if mode == "exact":
+        keys = torch.empty(N, F, device=table.device, dtype=torch.int64)
+        call("r4r_conv_pool_simt", _p(table), V, E, _p(idx), N, T, _p(conv_w), _p(conv_b), F,
+             _p(pooled), _p(argmax), _p(keys), _stream())
+    else:
+        shadow = shadow if shadow is not None else ShadowTable()
+        sh = shadow.get(table, mode)
+        dt = _lib.R4R_DT_F16 if mode == "f16" else _lib.R4R_DT_BF16
+        nbytes = _lib.lib.r4r_conv_wpack_bytes(E, F)
+        if nbytes <= 0:
+            raise RuntimeError("conv_pool_tc: unsupported shape E=%d F=%d" % (E, F))
+        wpack = torch.empty(nbytes, device=table.device, dtype=torch.uint8)
+        call("r4r_conv_pack_weights", _p(conv_w), E, F, _p(wpack), dt, _stream())
+        call("r4r_conv_pool_tc", _p(sh), V, shadow.epad, E, dt, _p(idx), N, T, _p(wpack), _p(conv_b), F,
+             _p(pooled), _p(argmax), _stream())
+    return pooled, argmax
+
+
+class _ConvPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, idx, table, conv_w, conv_b, mode, shadow):
+        if table.requires_grad:
+            raise RuntimeError("the word table is frozen in the reference (DeepCoNN.py:15 freeze=True); "
+                               "a trainable word table is not part of this path")
+        pooled, argmax = conv_pool_forward(idx, table, conv_w, conv_b, mode, shadow)
+        ctx.save_for_backward(idx, table, argmax, pooled)
+        ctx.wshape = tuple(conv_w.shape)
+        ctx.mark_non_differentiable(argmax)
+        return pooled, argmax
+
+    @staticmethod
+    def backward(ctx, gpooled, _gargmax):
+        idx, table, argmax, pooled = ctx.saved_tensors
+        F, _, _, E = ctx.wshape
+        N, T = idx.shape
+        dW = torch.zeros(ctx.wshape, device=table.device, dtype=torch.float32)
+        db = torch.zeros(F, device=table.device, dtype=torch.float32)
+        call("r4r_conv_wgrad_argmax", _p(table), table.shape[0], E, _p(idx), N, T, _p(argmax), _p(pooled),
+             _p(_f32c(gpooled)), F, _p(dW), _p(db), _stream())
+        return None, None, dW, db, None, None
+
+
+def conv_pool(idx, table, conv_w, conv_b, mode=None, shadow=None):
+    pooled, _ = _ConvPool.apply(idx, table, conv_w, conv_b, mode or _conv_mode, shadow)
+    return pooled
+
+
+# ------------------------------------------------------------------------------------ linear
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W, b):
+        _need_cuda(x, W, b)
+        x, W = _f32c(x), _f32c(W)
+        b = _f32c(b) if b is not None else None
+        n, in_f = x.shape
+        out_f = W.shape[0]
+        y = torch.empty(n, out_f, device=x.device, dtype=torch.float32)
+        call("r4r_linear_fwd", _p(x), _p(W), _p(b), n, in_f, out_f, _p(y), _stream())
+        ctx.save_for_backward(x, W)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, W = ctx.saved_tensors
+        gy = _f32c(gy)
+        n, in_f = x.shape
+        out_f = W.shape[0]
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dW = torch.zeros_like(W) if ctx.needs_input_grad[1] else None
+        db = torch.zeros(out_f, device=x.device, dtype=torch.float32) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        call("r4r_linear_bwd", _p(x), _p(W), _p(gy), n, in_f, out_f, _p(dx), _p(dW), _p(db), _stream())
+        return dx, dW, db
+
+
+def linear(x: torch.Tensor, W: torch.Tensor, b: Optional[torch.Tensor]) -> torch.Tensor:
+    """nn.Linear over the last dim; leading dims are flattened for the kernel."""
+    lead = x.shape[:-1]
+    y = _Linear.apply(x.reshape(-1, x.shape[-1]), W, b)
+    return y.reshape(*lead, W.shape[0])
+
+
+# ------------------------------------------------------------------------------------ FM
+class _FM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, V, lin_w, lin_b):
+        _need_cuda(x, V, lin_w, lin_b)
+        x, V, lin_w, lin_b = _f32c(x), _f32c(V), _f32c(lin_w), _f32c(lin_b)
+        n, nf = x.shape
+        k = V.shape[1]
+        out = torch.empty(n, device=x.device, dtype=torch.float32)
+        call("r4r_fm_fwd", _p(x), _p(V), _p(lin_w), _p(lin_b), n, nf, k, _p(out), _stream())
+        ctx.save_for_backward(x, V, lin_w)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, V, lin_w = ctx.saved_tensors
+        n, nf = x.shape
+        k = V.shape[1]
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dV = torch.zeros_like(V)
+        dw = torch.zeros_like(lin_w)
+        db = torch.zeros(1, device=x.device, dtype=torch.float32)
+        call("r4r_fm_bwd", _p(x), _p(V), _p(lin_w), _p(_f32c(gout)), n, nf, k, _p(dx), _p(dV), _p(dw), _p(db), _stream())
+        return dx, dV, dw, db
+
+
+def fm(x, V, lin_w, lin_b) -> torch.Tensor:
+    """TorchFM.forward (common_pytorch_models.py:49-57); returns [n,1] like the reference."""
+    return _FM.apply(x, V, lin_w, lin_b).unsqueeze(1)
+
+
+# ------------------------------------------------------------------------------------ MSE
+class _MSE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, out, y):
+        _need_cuda(out, y)
+        shape = out.shape
+        o, t = _f32c(out).reshape(-1), _f32c(y.expand_as(out)).reshape(-1)
+        se = torch.empty_like(o)
+        call("r4r_mse_fwd", _p(o), _p(t), o.numel(), _p(se), _p(None), _stream())
+        ctx.save_for_backward(o, t)
+        ctx.shape = shape
+        return se.reshape(shape)
+
+    @staticmethod
+    def backward(ctx, gse):
+        o, t = ctx.saved_tensors
+        g = torch.empty_like(o)
+        call("r4r_mse_bwd", _p(o), _p(t), _p(_f32c(gse).reshape(-1)), o.numel(), _p(g), _stream())
+        return g.reshape(ctx.shape), None
+
+
+def squared_error(out, y):
+    return _MSE.apply(out, y)
+
+
+# ------------------------------------------------------------------------------------ id rows
+class _RowsGather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, table, ids):
+        _need_cuda(table, ids)
+        table, ids = _f32c(table), _i64c(ids)
+        L = 1 if table.dim() == 1 else table.shape[1]
+        n = ids.numel()
+        out = torch.empty((n,) if table.dim() == 1 else (n, L), device=table.device, dtype=torch.float32)
+        call("r4r_rows_gather", _p(table), table.shape[0], L, _p(ids), n, _p(out), _stream())
+        ctx.save_for_backward(ids)
+        ctx.tshape = tuple(table.shape)
+        return out.reshape(*ids.shape) if table.dim() == 1 else out.reshape(*ids.shape, L)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (ids,) = ctx.saved_tensors
+        L = 1 if len(ctx.tshape) == 1 else ctx.tshape[1]
+        # dense gradient, as nn.Embedding(sparse=False) / Tensor.gather produce (SURVEY.md finding 5)
+        gtable = torch.zeros(ctx.tshape, device=gout.device, dtype=torch.float32)
+        call("r4r_rows_scatter_add", _p(_f32c(gout)), _p(ids), ids.numel(), L, _p(gtable), ctx.tshape[0], _stream())
+        return gtable, None
+
+
+def rows_gather(table, ids):
+    """table[ids] for an id-embedding matrix [R,L] or a bias vector [R]."""
+    return _RowsGather.apply(table, ids)

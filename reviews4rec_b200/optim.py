@@ -1,0 +1,48 @@
+"""FusedAdam: torch.optim.Adam semantics as the reference configures it (main.py:94-96) -- dense
+update of every parameter that has a gradient, L2 weight decay folded into the gradient, bias
+correction -- executed by ONE multi-tensor kernel launch (r4r_adam_step) per 48 tensors instead
+of torch's per-op foreach sweep.  Parameters whose ``.grad`` is None are skipped and their step
+count does not advance, exactly like torch (SURVEY.md 7 "dense-Adam semantics")."""
+import ctypes
+
+import torch
+
+from ._lib import call
+from .ops import _stream
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        for group in self.param_groups:
+            by_step = {}
+            for p in group["params"]:
+                if p.grad is None or p.numel() == 0:
+                    continue
+                if not p.is_cuda:
+                    raise RuntimeError("FusedAdam runs on CUDA parameters only (no CPU fallback)")
+                if p.dtype != torch.float32 or not p.is_contiguous():
+                    raise RuntimeError("FusedAdam expects contiguous float32 parameters")
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                st["step"] += 1
+                by_step.setdefault(st["step"], []).append(p)
+            b1, b2 = group["betas"]
+            for step, ps in by_step.items():
+                n = len(ps)
+                arr = ctypes.c_void_p * n
+                P = arr(*[p.data_ptr() for p in ps])
+                G = arr(*[p.grad.contiguous().data_ptr() for p in ps])
+                M = arr(*[self.state[p]["exp_avg"].data_ptr() for p in ps])
+                V = arr(*[self.state[p]["exp_avg_sq"].data_ptr() for p in ps])
+                NUM = (ctypes.c_int64 * n)(*[p.numel() for p in ps])
+                call("r4r_adam_step", n, P, G, M, V, NUM, step, ctypes.c_void_p(0), group["lr"], b1, b2,
+                     group["eps"], group["weight_decay"], _stream())
+        return loss

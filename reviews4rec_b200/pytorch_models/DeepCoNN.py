@@ -1,0 +1,39 @@
+"""DeepCoNN / DeepCoNN++ with the reference's constructor, forward(data) and state_dict
+(pytorch_models/DeepCoNN.py:9-72)."""
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..utils import load_obj
+from .common_pytorch_models import SmallLinear, TextCNN, TorchFM, WordTable
+
+
+class DeepCoNN(nn.Module):
+    def __init__(self, hyper_params):
+        super().__init__()
+        self.hyper_params = hyper_params
+        L = hyper_params["latent_size"]
+        self.word2vec = WordTable.from_vectors(load_obj(hyper_params["data_dir"] + "/word2vec"))
+        self.user_conv = TextCNN(hyper_params)
+        self.item_conv = TextCNN(hyper_params)
+        self.final = nn.Sequential(SmallLinear(2 * L, L), nn.ReLU(), nn.Dropout(hyper_params["dropout"]), SmallLinear(L, 1))
+        self.user_bias = nn.Parameter(torch.full((hyper_params["total_users"] + 2,), 0.1))
+        self.item_bias = nn.Parameter(torch.full((hyper_params["total_items"] + 2,), 0.1))
+        self.global_bias = nn.Parameter(torch.full((1,), 4.0))
+        self.fm = TorchFM(2 * L, 8)
+        self.dropout = nn.Dropout(hyper_params["dropout"])
+        self.relu = nn.ReLU()
+
+    def forward(self, data):
+        _, _, _, user_reviews, item_reviews, user_id, item_id = data
+        final_shape = tuple(user_id.shape)                      # [B] or [B,n] (ranking, eval.py:64-92)
+        first_dim = user_id.numel()
+        user = self.user_conv(self.word2vec(user_reviews.reshape(first_dim, -1)))
+        item = self.item_conv(self.word2vec(item_reviews.reshape(first_dim, -1)))
+        cat = torch.cat([user, item], dim=-1)
+        if self.hyper_params["model_type"] == "deepconn":
+            return (self.global_bias + self.fm(cat)[:, 0]).view(final_shape)
+        rating = self.final(cat)[:, 0]
+        ub = ops.rows_gather(self.user_bias, user_id.reshape(-1))
+        ib = ops.rows_gather(self.item_bias, item_id.reshape(-1))
+        return (rating + ub + ib + self.global_bias).view(final_shape)

@@ -1,0 +1,78 @@
+"""The training driver of the hot path with the reference's signature and metrics
+(main.py:8-71 ``train``), plus the restated TransNet step.
+
+``train`` is interchangeable with the reference's own ``main.train`` -- the model classes of this
+package also run unmodified under the reference's loop.  Differences, both documented in
+SURVEY.md section 8: (1) the per-batch ``float(torch.sum(loss))`` D2H sync (main.py:57) is replaced
+by a device-side accumulator read once per epoch; (2) the TransNet branch, which raises on
+torch >= 1.5 in the reference (in-place optimizer step between ``backward(retain_graph=True)``
+calls), is the exact restatement: three ``autograd.grad`` calls on one graph, then the three
+optimizer steps in the reference's order (target, source, source_fm).
+"""
+import torch
+
+TRANSNET = ("transnet", "transnet++")
+
+
+def _transnet_param_groups(model, hyper_params):
+    src = list(model.source.parameters())
+    sfm = list(model.source_fm.parameters())
+    if hyper_params["model_type"] == "transnet++":
+        sfm += [model.user_embedding.weight, model.item_embedding.weight]
+    tgt = [p for p in model.target.parameters() if p.requires_grad]
+    return src, sfm, tgt
+
+
+def transnet_step(model, criterion, optimizer, data, y, hyper_params):
+    """One TransNet batch (main.py:35-53 restated).  Returns (per-sample source SE, loss_target, loss_transform)."""
+    optimizer_source, optimizer_source_fm, optimizer_target = optimizer[0], optimizer[1], optimizer[2]
+    src, sfm, tgt = _transnet_param_groups(model, hyper_params)
+    out = model(data)
+    loss_target = criterion(out[1], y)
+    loss_transform = out[2]
+    se_source = criterion(out[0], y, return_mean=False)
+    g_t = torch.autograd.grad(loss_target, tgt, retain_graph=True, allow_unused=True)
+    g_s = torch.autograd.grad(loss_transform, src, retain_graph=True, allow_unused=True)
+    g_f = torch.autograd.grad(torch.mean(se_source), sfm, allow_unused=True)
+    for params, grads, opt in ((tgt, g_t, optimizer_target), (src, g_s, optimizer_source), (sfm, g_f, optimizer_source_fm)):
+        for p, g in zip(params, grads):
+            p.grad = g
+        opt.step()
+        for p in params:
+            p.grad = None
+    return se_source.detach(), loss_target.detach(), loss_transform.detach()
+
+
+def train(model, criterion, optimizer, reader, hyper_params):
+    """One epoch over ``reader.iter()``; returns ``{'MSE': round(sum SE / N, 4), ...}`` like main.py:66-71."""
+    model.train()
+    is_tn = hyper_params["model_type"] in TRANSNET
+    dev = next(model.parameters()).device
+    acc = torch.zeros(3, device=dev, dtype=torch.float64)       # sum SE, sum loss_target, sum loss_transform
+    total_x, total_batches = 0.0, 0.0
+    for data, y in reader.iter():
+        model.zero_grad()
+        if is_tn:
+            for o in optimizer:
+                o.zero_grad()
+            se, lt, lx = transnet_step(model, criterion, optimizer, data, y, hyper_params)
+            acc[0] += se.sum()
+            acc[1] += lt
+            acc[2] += lx
+            total_x += float(int(se.shape[0]))
+        else:
+            optimizer.zero_grad()
+            out = model(data)
+            loss = criterion(out, y, return_mean=False)
+            acc[0] += loss.detach().sum()
+            torch.mean(loss).backward()
+            optimizer.step()
+            total_x += float(int(out.shape[0]))
+        total_batches += 1
+    sums = acc.tolist()                                          # the only D2H sync of the epoch
+    metrics = {"MSE": round(sums[0] / float(total_x), 4)}
+    if is_tn:
+        metrics["MSE_target"] = round(sums[1] / float(total_batches), 4)
+        metrics["MSE_transform"] = round(sums[2] / float(total_batches), 4)
+    train.last_raw = {"se_sum": sums[0], "target_sum": sums[1], "transform_sum": sums[2], "n": total_x, "batches": total_batches}
+    return metrics

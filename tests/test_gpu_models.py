@@ -1,0 +1,160 @@
+"""Model-level parity on the GPU against the golden vectors produced by the unmodified reference
+(tests/golden/*.npz) and against the CPU oracle: forward (1-D and ranking-shaped ids), first-batch
+gradients, post-Adam parameters and train-loop MSE, through the package's drop-in module classes.
+
+Tolerances: ratings / MSE 1e-4 relative (north_star); gradients and post-Adam parameters
+rel 1e-4 + abs 1e-5/2e-6 in 'exact' mode (summation order differs from ATen's)."""
+import os
+import pickle
+import tempfile
+
+import pytest
+import torch
+
+from tests.helpers import (MODEL_TYPES, assert_close, golden_batches, golden_data, golden_hp, golden_state,
+                           load_golden)
+
+pytestmark = pytest.mark.gpu
+
+
+class ListReader:
+    def __init__(self, batches):
+        self.batches = batches
+
+    def iter(self, eval=False):
+        yield from self.batches
+
+    def __len__(self):
+        return len(self.batches)
+
+
+def build(mt, z, dims, mode="exact", dropout=0.0):
+    import reviews4rec_b200 as R
+    from reviews4rec_b200 import ops
+    ops.set_conv_mode(mode)
+    tmp = tempfile.mkdtemp()
+    with open(os.path.join(tmp, "word2vec.pkl"), "wb") as f:
+        pickle.dump(torch.zeros(dims["V"], dims["E"]).tolist(), f, 2)
+    hp = golden_hp(mt, dims, dropout)
+    hp["data_dir"] = tmp
+    cls = {"deepconn": R.DeepCoNN, "deepconn++": R.DeepCoNN, "NARRE": R.NARRE, "transnet": R.TransNet,
+           "transnet++": R.TransNet}.get(mt, R.MF)
+    model = cls(hp)
+    model.load_state_dict(golden_state(z, "init"))            # state_dict keys/shapes are the contract
+    return model.cuda(), hp
+
+
+def as_list(o):
+    return o if isinstance(o, list) else [o]
+
+
+@pytest.mark.parametrize("mode", ["exact", "f16"])
+@pytest.mark.parametrize("mt", MODEL_TYPES)
+def test_eval_forward_vs_reference(mt, mode):
+    z, dims = load_golden(mt)
+    model, hp = build(mt, z, dims, mode, dropout=0.6)
+    model.eval()
+    with torch.no_grad():
+        out = as_list(model(golden_data(z, "b0", "cuda")))
+        rk = as_list(model(golden_data(z, "rank", "cuda")))
+    for j, o in enumerate(out):
+        assert_close(o, z["eval.out%d" % j], rtol=1e-4, atol=1e-5, msg="%s eval.out%d" % (mt, j))
+    for j, o in enumerate(rk):
+        assert tuple(o.shape) == tuple(z["rank.out%d" % j].shape)
+        assert_close(o, z["rank.out%d" % j], rtol=1e-4, atol=1e-5, msg="%s rank.out%d" % (mt, j))
+
+
+@pytest.mark.parametrize("mt", [m for m in MODEL_TYPES if not m.startswith("transnet")])
+def test_first_batch_grads_vs_reference(mt):
+    import reviews4rec_b200 as R
+    z, dims = load_golden(mt)
+    model, hp = build(mt, z, dims)
+    model.train()
+    data, y = golden_batches(z, dims, "cuda")[0]
+    out = model(data)
+    assert_close(out, z["train.out0"], rtol=1e-4, atol=1e-5, msg="train.out0")
+    R.MSELoss(hp)(out, y).backward()
+    ref = {k[5:]: z[k] for k in z.files if k.startswith("grad.")}
+    got = {n: p.grad for n, p in model.named_parameters() if p.grad is not None}
+    assert set(ref) == set(got), set(ref) ^ set(got)
+    for k in ref:
+        assert_close(got[k], ref[k], rtol=1e-4, atol=1e-6, msg=mt + " grad." + k)
+
+
+@pytest.mark.parametrize("opt_kind", ["torch", "fused"])
+@pytest.mark.parametrize("mt", MODEL_TYPES)
+def test_train_loop_vs_reference(mt, opt_kind):
+    import reviews4rec_b200 as R
+    from reviews4rec_b200.optim import FusedAdam
+    from reviews4rec_b200.train import train
+    from reviews4rec_b200.utils import init_transnet_optim
+    z, dims = load_golden(mt)
+    model, hp = build(mt, z, dims)
+    cls = torch.optim.Adam if opt_kind == "torch" else FusedAdam
+    if mt.startswith("transnet"):
+        opt = init_transnet_optim(hp, model, cls)
+    else:
+        opt = cls(model.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"])
+    metrics = train(model, R.MSELoss(hp), opt, ListReader(golden_batches(z, dims, "cuda")), hp)
+    raw = train.last_raw
+    assert raw["n"] == int(z["metric.N"])
+    if mt.startswith("transnet"):
+        assert_close(raw["se_sum"], float(z["metric.MSE_sum"]), rtol=1e-4, msg="MSE sum")
+        assert_close(raw["target_sum"], float(z["metric.MSE_target_sum"]), rtol=1e-4, msg="MSE_target sum")
+        assert_close(raw["transform_sum"], float(z["metric.MSE_transform_sum"]), rtol=1e-4, msg="MSE_transform sum")
+    else:
+        assert abs(metrics["MSE"] - float(z["metric.MSE"])) <= 1e-4 * max(1.0, abs(float(z["metric.MSE"])))
+    ref = golden_state(z, "final")
+    sd = model.state_dict()
+    for k in ref:
+        assert_close(sd[k], ref[k], rtol=1e-4, atol=4e-6, msg="%s final.%s" % (mt, k))
+
+
+def test_reference_loop_shape_contract():
+    """The drop-in classes expose what main.train / utils.init_transnet_optim touch."""
+    z, dims = load_golden("transnet++")
+    model, hp = build("transnet++", z, dims)
+    for attr in ("source", "target", "source_fm", "user_embedding", "item_embedding"):
+        assert hasattr(model, attr)
+    out = model(golden_data(z, "b0", "cuda"))
+    assert isinstance(out, list) and len(out) == 3 and out[2].dim() == 0
+    assert model.source.ir.shape == model.target.ir.shape == (dims["B"], dims["L"])
+    sd = model.state_dict()
+    model.load_state_dict(sd)
+
+
+@pytest.mark.parametrize("mt", ["deepconn", "deepconn++", "NARRE"])
+def test_oracle_agrees_at_larger_shapes(mt):
+    """Seeded mid-size problem (E=300, T=150): GPU module vs CPU oracle, eval forward + one train step."""
+    from oracle import r4r_oracle as O
+    import reviews4rec_b200 as R
+    from reviews4rec_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    V, E, L, U, I, B = 700, 300, 10, 50, 30, 16
+    hp = {"model_type": mt, "latent_size": L, "word_embed_size": E, "dropout": 0.0, "total_users": U, "total_items": I,
+          "lr": 0.002, "weight_decay": 1e-6}
+    P = O.init_params(hp, V, seed=3)
+    tmp = tempfile.mkdtemp()
+    with open(os.path.join(tmp, "word2vec.pkl"), "wb") as f:
+        pickle.dump(torch.zeros(V, E).tolist(), f, 2)
+    hp["data_dir"] = tmp
+    ops.set_conv_mode("exact")
+    model = (R.NARRE if mt == "NARRE" else R.DeepCoNN)(hp)
+    model.load_state_dict(P)
+    model = model.cuda()
+    ri = lambda hi, *s: torch.randint(0, hi, s, generator=g, dtype=torch.int64)
+    if mt == "NARRE":
+        data = [ri(V, B, 40), ri(U + 2, B, 4), ri(I + 2, B, 4), ri(V, B, 4, 40), ri(V, B, 4, 40), ri(U + 1, B), ri(I + 1, B)]
+    else:
+        data = [ri(V, B, 150), ri(U + 2, B, 10), ri(I + 2, B, 10), ri(V, B, 150), ri(V, B, 150), ri(U + 1, B), ri(I + 1, B)]
+    y = torch.randint(1, 6, (B,), generator=g).float()
+    out_ref, se_ref, grads = O.grads_of(P, data, y, hp, train=True)
+    model.train()
+    out = model([d.cuda() for d in data])
+    assert_close(out, out_ref, rtol=1e-4, atol=1e-5, msg="ratings")
+    R.MSELoss(hp)(out, y.cuda()).backward()
+    for n, p in model.named_parameters():
+        if grads.get(n) is not None:
+            assert_close(p.grad, grads[n], rtol=2e-4, atol=2e-6, msg="grad " + n)
+        else:
+            assert p.grad is None, n
