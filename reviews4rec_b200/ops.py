@@ -63,6 +63,8 @@ def word_gather(table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     _need_cuda(table, idx)
     table, idx = _f32c(table), _i64c(idx)
     out = torch.empty(*idx.shape, table.shape[1], device=table.device, dtype=torch.float32)
+    if idx.numel() == 0:
+        return out
     call("r4r_word_gather_f32", _p(table), table.shape[0], table.shape[1], _p(idx), idx.numel(), _p(out), _stream())
     return out
 

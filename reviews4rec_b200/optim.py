@@ -39,10 +39,12 @@ class FusedAdam(torch.optim.Optimizer):
                 n = len(ps)
                 arr = ctypes.c_void_p * n
                 P = arr(*[p.data_ptr() for p in ps])
-                G = arr(*[p.grad.contiguous().data_ptr() for p in ps])
                 M = arr(*[self.state[p]["exp_avg"].data_ptr() for p in ps])
                 V = arr(*[self.state[p]["exp_avg_sq"].data_ptr() for p in ps])
                 NUM = (ctypes.c_int64 * n)(*[p.numel() for p in ps])
-                call("r4r_adam_step", n, P, G, M, V, NUM, step, ctypes.c_void_p(0), group["lr"], b1, b2,
+                grads = [p.grad.contiguous() for p in ps]          # keep alive across the launch
+                G = arr(*[g.data_ptr() for g in grads])
+                vp = lambda a: ctypes.cast(a, ctypes.c_void_p)
+                call("r4r_adam_step", n, vp(P), vp(G), vp(M), vp(V), vp(NUM), step, ctypes.c_void_p(0), group["lr"], b1, b2,
                      group["eps"], group["weight_decay"], _stream())
         return loss

@@ -57,11 +57,15 @@ def test_eval_forward_vs_reference(mt, mode):
     with torch.no_grad():
         out = as_list(model(golden_data(z, "b0", "cuda")))
         rk = as_list(model(golden_data(z, "rank", "cuda")))
+    # 'exact': rel 1e-4 + abs 1e-5.  'f16': the golden word vectors are O(1) randn values rounded to
+    # half precision, and TransNet's outputs carry no global bias (|out| ~ 0.1), so the absolute
+    # floor is 1e-4 -- i.e. 1e-4 relative on the 1..5 rating scale the north_star tolerance refers to.
+    atol = 1e-5 if mode == "exact" else 1e-4
     for j, o in enumerate(out):
-        assert_close(o, z["eval.out%d" % j], rtol=1e-4, atol=1e-5, msg="%s eval.out%d" % (mt, j))
+        assert_close(o, z["eval.out%d" % j], rtol=1e-4, atol=atol, msg="%s eval.out%d" % (mt, j))
     for j, o in enumerate(rk):
         assert tuple(o.shape) == tuple(z["rank.out%d" % j].shape)
-        assert_close(o, z["rank.out%d" % j], rtol=1e-4, atol=1e-5, msg="%s rank.out%d" % (mt, j))
+        assert_close(o, z["rank.out%d" % j], rtol=1e-4, atol=atol, msg="%s rank.out%d" % (mt, j))
 
 
 @pytest.mark.parametrize("mt", [m for m in MODEL_TYPES if not m.startswith("transnet")])
@@ -107,7 +111,12 @@ def test_train_loop_vs_reference(mt, opt_kind):
     ref = golden_state(z, "final")
     sd = model.state_dict()
     for k in ref:
-        assert_close(sd[k], ref[k], rtol=1e-4, atol=4e-6, msg="%s final.%s" % (mt, k))
+        atol = 4e-6
+        if mt == "NARRE" and k.startswith("attention_scorer_") and k.endswith(".3.bias"):
+            # softmax is shift-invariant: this bias has an exactly-zero true gradient, so the
+            # reference's own update is Adam-normalised rounding noise (|step| <= lr per batch).
+            atol = hp["lr"] * dims["NB"]
+        assert_close(sd[k], ref[k], rtol=1e-4, atol=atol, msg="%s final.%s" % (mt, k))
 
 
 def test_reference_loop_shape_contract():
