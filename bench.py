@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py -- train ratings/sec of the DeepCoNN rating-prediction hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (this repo's sm_100a path)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (reference algorithm, host cores)
+
+Workload = BASELINE.json configs[1]: DeepCoNN (`deepconn`, FM head), word_emb E=300, 100 conv
+filters, doc_len T=1000, latent 10, V=50,001 words, 1M users / 100k items, synthetic Amazon-shaped
+batches (reviews4rec_b200/synthetic.py).  A step = one training batch through main.train()'s body:
+forward, per-sample squared error, backward, Adam (lr 0.002, weight_decay 1e-6, dropout 0.6).
+
+One JSON line on stdout (rank 0):
+  value     ratings/s with the batches already resident in HBM (a pool larger than L2, cycled)
+  e2e       ratings/s through the public API from pinned HOST batches: H2D of the batch and D2H of
+            the batch's squared-error sum are inside the timed region, every step
+  roofline  the dominant kernel (fused gather+conv+pool): algorithmic bytes per launch / its
+            CUDA-event duration inside the timed region, against MEASURED_PEAKS.json
+  cpu_baseline  the oracle's CPU restatement of the same step on a bounded sample (N=1 only)
+"""
+import argparse
+import json
+import os
+import pickle
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+V_WORDS = 50001
+HP = {"model_type": "deepconn", "latent_size": 10, "word_embed_size": 300, "input_length": 1000, "dropout": 0.6,
+      "total_users": 1000000, "total_items": 100000, "lr": 0.002, "weight_decay": 1e-6, "batch_size": 4096,
+      "narre_num_reviews": 10, "narre_num_words": 200}
+METRIC = "train ratings/sec DeepCoNN synthetic Amazon-shape"
+REF_SAMPLE_B = 128            # ratings per reference-arm step (the reference's own default batch, hyper_params.py:60)
+
+
+def algorithmic_bytes_per_rating(hp):
+    """bytes that must cross HBM once, as the reference stores them
+    (int64 token id + fp32 row per token, two docs; ids + rating + rating out)."""
+    T, E = hp["input_length"], hp["word_embed_size"]
+    return 2 * T * (8 + 4 * E) + 2 * 8 + 4 + 4
+
+
+def conv_flops_per_doc(hp):
+    return 2.0 * (hp["input_length"] + 2) * 100 * 3 * hp["word_embed_size"]
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            m = json.load(f)
+        return float(m["hbm_gbs"]), float(m.get("bf16_tflops_sustained", m["bf16_tflops"])), "measured"
+    except Exception:
+        return 6650.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".clocks.csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def oracle_params_from(model_state):
+    return {k: v.detach().to("cpu").clone() for k, v in model_state.items()}
+
+
+def cpu_train_rate(P, hp, n_steps, warmup, seed, budget_s=None):
+    """Times the oracle's restatement of main.train()'s batch body (oracle/r4r_oracle.py::train_batches,
+    same ATen CPU kernels the reference dispatches) on REF_SAMPLE_B-rating batches.  Returns (ratings/s, ms/step, steps)."""
+    import torch
+    from oracle import r4r_oracle as O          # reference arm / cpu_baseline: the one place bench.py runs the oracle
+    from reviews4rec_b200.synthetic import SyntheticReader
+    hp = dict(hp)
+    reader = SyntheticReader(hp, REF_SAMPLE_B, max(1, min(4, n_steps)), V_WORDS, seed=seed)
+    batches = reader.batches
+    opt = None
+    for i in range(warmup):
+        _, _, _, opt = O.train_batches(P, [batches[i % len(batches)]], hp, opt=opt)
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(n_steps):
+        _, _, _, opt = O.train_batches(P, [batches[i % len(batches)]], hp, opt=opt)
+        done += 1
+        if budget_s is not None and done >= 3 and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return done * REF_SAMPLE_B / dt, dt / done * 1e3, done
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import r4r_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    hp = dict(HP)
+    P = O.init_params(hp, V_WORDS, seed=1)
+    rate, ms, steps = cpu_train_rate(P, hp, args.steps, args.warmup, seed=1234)
+    sample = "%d-rating batches (reference default batch_size) of the same synthetic workload, %d timed steps" % (REF_SAMPLE_B, steps)
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "ratings/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "DeepCoNN E=300 F=100 T=1000 L=10 V=50001 U=1M I=100k (BASELINE configs[1])",
+                       "batch": REF_SAMPLE_B, "threads": cores},
+            "cpu_baseline": {"value": rate, "unit": "ratings/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": "ratings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def build_model(hp, device, seed):
+    import numpy as np
+    import torch
+    import reviews4rec_b200 as R
+    from reviews4rec_b200.utils import xavier_init
+    tmp = tempfile.mkdtemp(prefix="r4r_bench_")
+    with open(os.path.join(tmp, "word2vec.pkl"), "wb") as f:           # values are overwritten by xavier_init (finding 2)
+        pickle.dump(np.zeros((V_WORDS, hp["word_embed_size"]), dtype=np.float32), f, 4)
+    hp["data_dir"] = tmp
+    torch.manual_seed(seed)
+    model = R.DeepCoNN(hp)
+    xavier_init(model)                                                  # main.py:377
+    return model.to(device)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from reviews4rec_b200 import MSELoss, _lib, ops
+    from reviews4rec_b200.optim import FusedAdam
+    from reviews4rec_b200.synthetic import SyntheticReader
+    from reviews4rec_b200.train import CapturedStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+
+    hp = dict(HP)
+    hp["batch_size"] = args.batch
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    ops.set_conv_mode(args.conv_mode)
+    model = build_model(hp, dev, seed=1)                   # same seed on every rank: replicas start identical
+    model.train()
+    criterion = MSELoss(hp)
+    opt = FusedAdam(model.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"], capturable=True)
+
+    # resident pool: POOL batches x (2 docs x B x T x 8 B); > L2 (126 MB) so inputs are cold every step
+    per_batch = 2 * B * hp["input_length"] * 8
+    pool_n = max(2, min(8, -(-160 * 2 ** 20 // per_batch)))
+    res = SyntheticReader(hp, B, pool_n, V_WORDS, seed=1234, device=dev, rank=rank)
+    host = SyntheticReader(hp, B, pool_n, V_WORDS, seed=4321, device=None, pin=True, rank=rank)
+
+    se_sum = torch.zeros(1, device=dev, dtype=torch.float32)
+    conv_events = []
+    ops.set_conv_event_sink(conv_events)
+    launches0 = _lib.launch_count
+    steps_res = [CapturedStep(model, criterion, opt, d, y, se_sum, group, float(world)) for d, y in res.batches]
+    launches_per_step = (_lib.launch_count - launches0) // len(steps_res)
+    res_events = list(conv_events)
+    ops.set_conv_event_sink(None)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident inputs
+    for i in range(W):
+        steps_res[i % pool_n].replay()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    se_sum.zero_()
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(K):
+        steps_res[i % pool_n].replay()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    train_mse = float(se_sum.item()) / (K * B)
+    # dominant kernel: duration of its launches in the last min(K, pool) steps of the timed region
+    used = min(K, pool_n)
+    conv_ms = []
+    try:
+        for j in range(used):
+            slot = (K - 1 - j) % pool_n
+            per = len(res_events) // pool_n                     # eager warm pass + captured pass per slot; the captured pair is last
+            for a, b in res_events[per * slot + per - 2: per * slot + per]:
+                conv_ms.append(a.elapsed_time(b))
+    except Exception as exc:                                       # external event nodes unsupported -> measured below
+        conv_ms = []
+        conv_err = repr(exc)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * B * K / (ms_total * 1e-3)
+
+    # ---- e2e: pinned host batches -> H2D (copy stream, double-buffered) -> captured step -> D2H of the SE sum
+    static = []
+    for s in range(2):
+        d0, y0 = res.batches[s]
+        static.append(([None if x is None else torch.empty_like(x) for x in d0], torch.empty_like(y0)))
+    se_e2e = torch.zeros(1, device=dev, dtype=torch.float32)
+    steps_e2e = [CapturedStep(model, criterion, opt, d, y, se_e2e, group, float(world)) for d, y in static]
+    copy_stream = torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+    ready = [torch.cuda.Event() for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
+    se_host = torch.zeros(max(K, W), dtype=torch.float32).pin_memory()
+    h2d = host.bytes_per_batch()
+
+    def e2e_loop(n):
+        for i in range(n):
+            s = i & 1
+            hd, hy = host.batches[i % pool_n]
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done[s])
+                for dst, src in zip(static[s][0], hd):
+                    if dst is not None:
+                        dst.copy_(src, non_blocking=True)
+                static[s][1].copy_(hy, non_blocking=True)
+                ready[s].record(copy_stream)
+            main.wait_event(ready[s])
+            steps_e2e[s].replay()
+            done[s].record(main)
+            se_host[i:i + 1].copy_(se_e2e, non_blocking=True)     # running SE sum, read back every step (main.py:57)
+
+    e2e_loop(W)
+    barrier()
+    se_e2e.zero_()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0.record()
+    e2e_loop(K)
+    e1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e0.elapsed_time(e1), 0.0)
+    t = torch.tensor([e2e_ms, wall_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t[0].item())
+    e2e_value = world * B * K / (e2e_ms * 1e-3)
+
+    # ---- dominant kernel timed stand-alone if the in-graph events were unavailable
+    timing = "cuda events bracketing the kernel inside the captured step, last %d steps of the timed region" % used
+    if not conv_ms:
+        d, y = res.batches[0]
+        conv = model.user_conv.convs[0]
+        with torch.no_grad():
+            for i in range(3):
+                ops.conv_pool_forward(d[3], model.word2vec.weight, conv.weight, conv.bias, args.conv_mode, model.word2vec._shadow)
+            for i in range(min(K, pool_n)):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                sink = []
+                ops.set_conv_event_sink(sink)
+                ops.conv_pool_forward(res.batches[i][0][3], model.word2vec.weight, conv.weight, conv.bias, args.conv_mode, model.word2vec._shadow)
+                ops.set_conv_event_sink(None)
+                torch.cuda.synchronize()
+                conv_ms.append(sink[0][0].elapsed_time(sink[0][1]))
+        timing = "cuda events around stand-alone launches on the bench batches (in-graph events unavailable)"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, tf_peak, peak_kind = measured_peaks()
+    conv_avg_ms = sum(conv_ms) / len(conv_ms)
+    bytes_per_launch = B * hp["input_length"] * (8 + 4 * hp["word_embed_size"])          # one tower = one doc per rating
+    achieved = bytes_per_launch / (conv_avg_ms * 1e-3) / 1e9
+    tflops = B * conv_flops_per_doc(hp) / (conv_avg_ms * 1e-3) / 1e12
+    step_ms = ms_total / K
+    line = {
+        "metric": METRIC, "value": value, "unit": "ratings/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"f16": "f16 operands / f32 accumulate", "bf16": "bf16 operands / f32 accumulate", "exact": "f32"}[args.conv_mode],
+        "data": "synthetic",
+        "config": {"workload": "DeepCoNN E=300 F=100 T=1000 L=10 V=50001 U=1M I=100k (BASELINE configs[1])",
+                   "batch_per_gpu": B, "global_batch": B * world, "conv_mode": args.conv_mode, "dropout": hp["dropout"],
+                   "parallelism": "dp%d (replicated frozen word table, dense-grad all-reduce)" % world if world > 1 else "single GPU",
+                   "l2_policy": "inputs larger than L2: %d resident batches x %.0f MB cycled" % (pool_n, per_batch / 2 ** 20),
+                   "step": "CUDA graph of zero_grad+forward+MSE+backward+Adam"},
+        "e2e": {"value": e2e_value, "unit": "ratings/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_ms / K, "wall_ms_per_step": float(t[1].item()) / K},
+        "gpu_launches": launches_per_step * K,
+        "roofline": {"kernel": "conv_pool_tc_kernel (fused word gather + TextCNN conv + ReLU + max-pool)", "bound": "hbm",
+                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                     "peak_kind": peak_kind, "ms_per_launch": conv_avg_ms, "launches_per_step": 2,
+                     "share_of_step": 2 * conv_avg_ms / step_ms, "timing": timing,
+                     "tensor_tflops": tflops, "tensor_peak": tf_peak, "tensor_frac": tflops / tf_peak},
+        "step_roofline": {"bytes_per_rating": algorithmic_bytes_per_rating(hp),
+                          "achieved_gbs": algorithmic_bytes_per_rating(hp) * value / world / 1e9,
+                          "frac_of_hbm_peak": algorithmic_bytes_per_rating(hp) * value / world / 1e9 / hbm_peak},
+        "train_mse": train_mse,
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        P = oracle_params_from(model.state_dict())
+        rate, ms, steps = cpu_train_rate(P, hp, 40, 1, seed=1234, budget_s=15.0)
+        line["cpu_baseline"] = {"value": rate, "unit": "ratings/s", "cores": cores, "kind": "port",
+                                "sample": "%d timed steps of %d ratings (same synthetic workload), oracle/r4r_oracle.py::train_batches" % (steps, REF_SAMPLE_B)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=HP["batch_size"], help="ratings per GPU per step")
+    ap.add_argument("--conv-mode", default="f16", choices=["f16", "bf16", "exact"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000)] + sys.argv
+        sys.exit(subprocess.call(cmd))
+    run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -119,6 +119,9 @@ int r4r_rows_scatter_add(const float* gout, const int64_t* ids, int64_t n, int L
 int r4r_adam_step(int nt, float* const* p_host, const float* const* g_host, float* const* m_host,
                   float* const* v_host, const int64_t* numel_host, int step, const int32_t* step_dev,
                   float lr, float beta1, float beta2, float eps, float weight_decay, void* stream);
+/* *counter += 1 on the device: the step count of a CUDA-graph-captured optimizer (torch keeps
+ * state['step'] as a device tensor for capturable=True; torch/optim/adam.py semantics). */
+int r4r_counter_inc(int32_t* counter, void* stream);
 
 #ifdef __cplusplus
 }

@@ -39,6 +39,7 @@ SIGNATURES = {
     "r4r_rows_gather": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_vp]),
     "r4r_rows_scatter_add": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_vp]),
     "r4r_adam_step": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp] + [c_f32] * 5 + [c_vp]),
+    "r4r_counter_inc": (c_int, [c_vp, c_vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

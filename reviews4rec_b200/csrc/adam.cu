@@ -110,3 +110,15 @@ extern "C" int r4r_adam_step(int nt, float* const* p_host, const float* const* g
   }
   return 0;
 }
+
+// Device-side step counter for CUDA-graph replays of the optimizer: *counter += 1.
+namespace {
+__global__ void counter_inc_kernel(int32_t* c) { *c += 1; }
+}  // namespace
+
+extern "C" int r4r_counter_inc(int32_t* counter, void* stream) {
+  R4R_REQUIRE(counter, R4R_EINVAL, "counter_inc: null pointer");
+  counter_inc_kernel<<<1, 1, 0, as_stream(stream)>>>(counter);
+  R4R_CHECK_LAUNCH("counter_inc");
+  return 0;
+}

@@ -30,6 +30,33 @@ def get_conv_mode() -> str:
     return _conv_mode
 
 
+# Optional measurement hook (bench.py): when a list is installed here, every launch of the dominant
+# kernel (r4r_conv_pool_tc / r4r_conv_pool_simt) is bracketed by a pair of timing CUDA events on the
+# launching stream; under graph capture they become external event-record nodes, re-recorded at
+# every replay.
+_conv_event_sink = None
+
+
+def set_conv_event_sink(sink):
+    global _conv_event_sink
+    _conv_event_sink = sink
+
+
+class _ConvTimer:
+    def __enter__(self):
+        self.on = _conv_event_sink is not None
+        if self.on:
+            ext = torch.cuda.is_current_stream_capturing()
+            self.e0 = torch.cuda.Event(enable_timing=True, external=ext)
+            self.e1 = torch.cuda.Event(enable_timing=True, external=ext)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.e1.record()
+            _conv_event_sink.append((self.e0, self.e1))
+
+
 def _p(t: Optional[torch.Tensor]):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
@@ -106,8 +133,9 @@ def conv_pool_forward(idx: torch.Tensor, table: torch.Tensor, conv_w: torch.Tens
     argmax = torch.empty(N, F, device=table.device, dtype=torch.int32)
     if mode == "exact":
         keys = torch.empty(N, F, device=table.device, dtype=torch.int64)
-        call("r4r_conv_pool_simt", _p(table), V, E, _p(idx), N, T, _p(conv_w), _p(conv_b), F,
-             _p(pooled), _p(argmax), _p(keys), _stream())
+        with _ConvTimer():
+            call("r4r_conv_pool_simt", _p(table), V, E, _p(idx), N, T, _p(conv_w), _p(conv_b), F,
+                 _p(pooled), _p(argmax), _p(keys), _stream())
     else:
         shadow = shadow if shadow is not None else ShadowTable()
         sh = shadow.get(table, mode)
@@ -117,8 +145,9 @@ def conv_pool_forward(idx: torch.Tensor, table: torch.Tensor, conv_w: torch.Tens
             raise RuntimeError("conv_pool_tc: unsupported shape E=%d F=%d" % (E, F))
         wpack = torch.empty(nbytes, device=table.device, dtype=torch.uint8)
         call("r4r_conv_pack_weights", _p(conv_w), E, F, _p(wpack), dt, _stream())
-        call("r4r_conv_pool_tc", _p(sh), V, shadow.epad, E, dt, _p(idx), N, T, _p(wpack), _p(conv_b), F,
-             _p(pooled), _p(argmax), _stream())
+        with _ConvTimer():
+            call("r4r_conv_pool_tc", _p(sh), V, shadow.epad, E, dt, _p(idx), N, T, _p(wpack), _p(conv_b), F,
+                 _p(pooled), _p(argmax), _stream())
     return pooled, argmax
 
 

@@ -76,3 +76,50 @@ def train(model, criterion, optimizer, reader, hyper_params):
         metrics["MSE_transform"] = round(sums[2] / float(total_batches), 4)
     train.last_raw = {"se_sum": sums[0], "target_sum": sums[1], "transform_sum": sums[2], "n": total_x, "batches": total_batches}
     return metrics
+
+
+class CapturedStep:
+    """One non-TransNet training batch of ``train()`` -- zero_grad, forward, per-sample SE, backward
+    of the mean, optional data-parallel gradient all-reduce, optimizer step (main.py:26-60) --
+    recorded ONCE into a CUDA graph over static input buffers and replayed per batch, so a step
+    costs one graph launch instead of ~40 Python-driven kernel launches.
+
+    ``data`` / ``y`` are the static device buffers the graph reads (copy each batch into them, or
+    build one CapturedStep per resident batch).  ``se_sum`` is a device scalar that every replay
+    ADDS the batch's sum of squared errors to (main.py:57 without its per-batch D2H sync).
+    The optimizer must be graph-safe: ``FusedAdam(capturable=True)``.
+    """
+
+    def __init__(self, model, criterion, optimizer, data, y, se_sum=None, group=None, grad_div=1.0):
+        import torch.distributed as dist
+
+        self.model, self.data, self.y = model, data, y
+        dev = y.device
+        self.se_sum = se_sum if se_sum is not None else torch.zeros(1, device=dev, dtype=torch.float32)
+        if hasattr(optimizer, "prepare"):
+            optimizer.prepare()
+        with torch.no_grad():
+            model(data)             # eager pass: builds the shadow word table and lazy kernel attributes outside the graph
+        model.zero_grad(set_to_none=True)
+        self.graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(self.graph):
+            out = model(data)
+            se = criterion(out, y, return_mean=False)
+            self.se_sum += se.detach().sum()
+            torch.mean(se).backward()
+            if group is not None:
+                grads = [p.grad for p in model.parameters() if p.grad is not None]
+                flat = torch.cat([g.reshape(-1) for g in grads])
+                dist.all_reduce(flat, group=group)
+                if grad_div != 1.0:
+                    flat /= grad_div
+                ofs = 0
+                for g in grads:
+                    g.copy_(flat[ofs:ofs + g.numel()].view_as(g))
+                    ofs += g.numel()
+            optimizer.step()
+        self.out = out
+
+    def replay(self):
+        self.graph.replay()
