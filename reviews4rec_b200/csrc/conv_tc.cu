@@ -28,6 +28,7 @@
 //   warp  8    MMA      : allocates TMEM, one elected lane issues tcgen05.mma, tcgen05.commit
 //                         releases ring slots ("empty") and publishes accumulators ("tmem_full")
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -83,8 +84,15 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+// .ca keeps the gathered lines in L1: the pad row (token 0, ~2/3 of all positions on Amazon-shaped
+// documents) and the Zipf head then hit in L1 instead of queueing on a handful of L2 lines.
+__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(unsigned long long* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (layout_type 0), version 1 (sm_100)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -130,6 +138,7 @@ struct Params {
   int fmt;                   // 0 f16, 1 bf16
   int nsplit;
   int nslots;
+  int ld_ca;                 // 1: cp.async.ca (L1-allocating) gathers, 0: cp.async.cg
   int nb[2];                 // filters (padded to 16) per split
   int f0[2];                 // first filter of each split
   long long wofs[2];         // byte offset of each split image in wpack
@@ -222,9 +231,12 @@ __device__ __forceinline__ void producer_role(const Params& P, SharedCtl* ctl, u
   const uint32_t ring_base = smem_u32(ring);
   const uint32_t dst_thread = (uint32_t)(c8 * RA * 16 + r0 * 16);
   const int nslots = P.nslots;
-  const int depth = nslots - 1;                          // slabs in flight per thread (cp.async groups)
 
-  uint32_t issued = 0, signalled = 0;
+  // Fully asynchronous hand-off: a thread never waits for its own copies.  After issuing the
+  // 16-byte gathers of a slab it posts cp.async.mbarrier.arrive.noinc on the slab's "full"
+  // barrier, which the hardware triggers once those copies have landed; the MMA warp orders the
+  // (generic-proxy) writes before its tensor-core reads with fence.proxy.async after the wait.
+  uint32_t issued = 0;
   for (long long doc = cta_in_split; doc < P.N; doc += ctas_in_split) {
     const long long* drow = P.idx + doc * (long long)P.T;
     for (int t = 0; t < ntiles; ++t) {
@@ -252,32 +264,16 @@ __device__ __forceinline__ void producer_role(const Params& P, SharedCtl* ctl, u
           for (int k = 0; k < ROWS_PER_THREAD; ++k) {
             if (r0 + 16 * k < TILE_M + 2) {
               const uint8_t* sp = src[k];
-              cp_async16(dst + k * 256, sp ? sp + ch * 16 : P.shadow, sp ? 16u : 0u);
+              if (P.ld_ca) cp_async16_ca(dst + k * 256, sp ? sp + ch * 16 : P.shadow, sp ? 16u : 0u);
+              else         cp_async16(dst + k * 256, sp ? sp + ch * 16 : P.shadow, sp ? 16u : 0u);
             }
           }
         }
-        cp_async_commit();
-        // slab (issued - depth) has landed once at most `depth` groups are still pending
-        if (issued + 1 - signalled > (uint32_t)depth) {
-          switch (depth) {
-            case 1: cp_async_wait<1>(); break;
-            case 2: cp_async_wait<2>(); break;
-            case 3: cp_async_wait<3>(); break;
-            case 4: cp_async_wait<4>(); break;
-            case 5: cp_async_wait<5>(); break;
-            case 6: cp_async_wait<6>(); break;
-            default: cp_async_wait<7>(); break;
-          }
-          fence_proxy_async();
-          mbar_arrive(&ctl->full[signalled % nslots]);
-          ++signalled;
-        }
+        cp_async_mbar_arrive_noinc(&ctl->full[slot]);
       }
     }
   }
-  cp_async_wait<0>();
-  fence_proxy_async();
-  for (; signalled < issued; ++signalled) mbar_arrive(&ctl->full[signalled % nslots]);
+  cp_async_wait_all();                                    // no copy may be in flight when the CTA exits
 }
 
 __device__ __forceinline__ void mma_role(const Params& P, SharedCtl* ctl, const uint8_t* bsm, const uint8_t* ring, int split,
@@ -299,6 +295,7 @@ __device__ __forceinline__ void mma_role(const Params& P, SharedCtl* ctl, const 
       for (int s = 0; s < spt; ++s, ++consumed) {
         const uint32_t slot = consumed % nslots, round = consumed / nslots;
         mbar_wait(&ctl->full[slot], round & 1u);
+        fence_proxy_async();                                   // producers' cp.async writes -> async proxy
         tc_fence_after();
         if (lane == 0) {
           const int nk = min(CPS, P.Kc - s * CPS) >> 1;        // K=16 steps in this slab
@@ -478,6 +475,10 @@ extern "C" int r4r_conv_pool_tc(const void* shadow, int64_t V, int Epad, int E, 
   P.wpack = static_cast<const uint8_t*>(wpack);
   P.bias = conv_b; P.pooled = pooled; P.argmax = argmax;
   P.fmt = dtype; P.nsplit = pl.nsplit; P.nslots = nslots;
+  {
+    const char* e = getenv("R4R_CONV_LD");
+    P.ld_ca = !(e && e[0] == 'c' && e[1] == 'g');
+  }
   for (int h = 0; h < 2; ++h) { P.nb[h] = pl.nb[h]; P.f0[h] = pl.f0[h]; P.wofs[h] = pl.wofs[h]; }
 
   R4R_CUDA(cudaFuncSetAttribute(conv_pool_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
