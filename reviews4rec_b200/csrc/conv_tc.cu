@@ -139,6 +139,7 @@ struct Params {
   int nsplit;
   int nslots;
   int ld_ca;                 // 1: cp.async.ca (L1-allocating) gathers, 0: cp.async.cg
+  int dbg;                   // perf experiments only (R4R_CONV_DBG): 1 no row shift, 2 no MMA, 4 no copies, 8 no epilogue compare
   int nb[2];                 // filters (padded to 16) per split
   int f0[2];                 // first filter of each split
   long long wofs[2];         // byte offset of each split image in wpack
@@ -176,7 +177,7 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, i
         uint32_t v[16];
         tmem_ld16(taddr + c0, v);
         tmem_ld_wait();
-        if (valid) {
+        if (valid && !(P.dbg & 8)) {
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
             float x = __uint_as_float(v[c]);
@@ -236,42 +237,56 @@ __device__ __forceinline__ void producer_role(const Params& P, SharedCtl* ctl, u
   // 16-byte gathers of a slab it posts cp.async.mbarrier.arrive.noinc on the slab's "full"
   // barrier, which the hardware triggers once those copies have landed; the MMA warp orders the
   // (generic-proxy) writes before its tensor-core reads with fence.proxy.async after the wait.
-  uint32_t issued = 0;
-  for (long long doc = cta_in_split; doc < P.N; doc += ctas_in_split) {
+  // Token ids of a tile's rows are fetched ONE TILE AHEAD into registers (unchecked, so the nine
+  // loads are issued back to back and their HBM latency hides behind the current tile's slabs);
+  // slot row r <-> document position t*128 - 2 + r, -1 marks a zero (padding) row.
+  auto fetch = [&](long long doc, int t, long long (&out)[ROWS_PER_THREAD]) {
     const long long* drow = P.idx + doc * (long long)P.T;
-    for (int t = 0; t < ntiles; ++t) {
-      // tokens of this thread's rows: slot row r <-> document position t*128 - 2 + r
-      const uint8_t* src[ROWS_PER_THREAD];
 #pragma unroll
-      for (int k = 0; k < ROWS_PER_THREAD; ++k) {
-        int r = r0 + 16 * k;
-        int pos = t * TILE_M - 2 + r;
-        const uint8_t* s = nullptr;
-        if (r < TILE_M + 2 && pos >= 0 && pos < P.T) {
-          long long tok = __ldg(drow + pos);
-          if (tok < 0 || tok >= P.V) __trap();
-          s = P.shadow + tok * P.row_bytes;
-        }
-        src[k] = s;
-      }
-      for (int s = 0; s < spt; ++s, ++issued) {
-        const uint32_t slot = issued % nslots, round = issued / nslots;
-        mbar_wait(&ctl->empty[slot], (round & 1u) ^ 1u);
-        const int ch = s * CPS + c8;
-        if (ch < P.Kc) {
-          const uint32_t dst = ring_base + slot * SLOT_BYTES + dst_thread;
+    for (int k = 0; k < ROWS_PER_THREAD; ++k) {
+      const int r = r0 + 16 * k;
+      const int pos = t * TILE_M - 2 + r;
+      out[k] = (r < TILE_M + 2 && pos >= 0 && pos < P.T) ? __ldg(drow + pos) : -1LL;
+    }
+  };
+  uint32_t issued = 0;
+  long long doc = cta_in_split;
+  int t = 0;
+  long long cur[ROWS_PER_THREAD], nxt[ROWS_PER_THREAD];
+  if (doc < P.N) fetch(doc, 0, cur);
+  while (doc < P.N) {
+    long long ndoc = doc;
+    int nt = t + 1;
+    if (nt == ntiles) { nt = 0; ndoc += ctas_in_split; }
+    if (ndoc < P.N) fetch(ndoc, nt, nxt);
+    const uint8_t* src[ROWS_PER_THREAD];
 #pragma unroll
-          for (int k = 0; k < ROWS_PER_THREAD; ++k) {
-            if (r0 + 16 * k < TILE_M + 2) {
-              const uint8_t* sp = src[k];
-              if (P.ld_ca) cp_async16_ca(dst + k * 256, sp ? sp + ch * 16 : P.shadow, sp ? 16u : 0u);
-              else         cp_async16(dst + k * 256, sp ? sp + ch * 16 : P.shadow, sp ? 16u : 0u);
-            }
+    for (int k = 0; k < ROWS_PER_THREAD; ++k) {
+      const long long tok = cur[k];
+      if (tok < -1 || tok >= P.V) __trap();               // the reference device-asserts on OOB ids
+      src[k] = tok < 0 ? nullptr : P.shadow + tok * P.row_bytes;
+    }
+    for (int s = 0; s < spt; ++s, ++issued) {
+      const uint32_t slot = issued % nslots, round = issued / nslots;
+      mbar_wait(&ctl->empty[slot], (round & 1u) ^ 1u);
+      const int ch = s * CPS + c8;
+      if (ch < P.Kc && !(P.dbg & 4)) {
+        const uint32_t dst = ring_base + slot * SLOT_BYTES + dst_thread;
+#pragma unroll
+        for (int k = 0; k < ROWS_PER_THREAD; ++k) {
+          if (r0 + 16 * k < TILE_M + 2) {
+            const uint8_t* sp = src[k];
+            if (P.ld_ca) cp_async16_ca(dst + k * 256, sp ? sp + ch * 16 : P.shadow, sp ? 16u : 0u);
+            else         cp_async16(dst + k * 256, sp ? sp + ch * 16 : P.shadow, sp ? 16u : 0u);
           }
         }
-        cp_async_mbar_arrive_noinc(&ctl->full[slot]);
       }
+      cp_async_mbar_arrive_noinc(&ctl->full[slot]);
     }
+#pragma unroll
+    for (int k = 0; k < ROWS_PER_THREAD; ++k) cur[k] = nxt[k];
+    doc = ndoc;
+    t = nt;
   }
   cp_async_wait_all();                                    // no copy may be in flight when the CTA exits
 }
@@ -302,9 +317,9 @@ __device__ __forceinline__ void mma_role(const Params& P, SharedCtl* ctl, const 
           for (int kk = 0; kk < nk; ++kk) {
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-              uint64_t ad = umma_desc(a_base + slot * SLOT_BYTES + (uint32_t)(2 * kk) * a_lbo + j * 16, a_lbo, 128);
+              uint64_t ad = umma_desc(a_base + slot * SLOT_BYTES + (uint32_t)(2 * kk) * a_lbo + ((P.dbg & 1) ? 0 : j * 16), a_lbo, 128);
               uint64_t bd = umma_desc(b_base + (uint32_t)(j * P.Kc + s * CPS + 2 * kk) * b_lbo, b_lbo, 128);
-              umma_f16(d_tmem, ad, bd, idesc, (s | kk | j) ? 1u : 0u);
+              if (!(P.dbg & 2)) umma_f16(d_tmem, ad, bd, idesc, (s | kk | j) ? 1u : 0u);
             }
           }
           umma_commit(&ctl->empty[slot]);                      // slot reusable once these MMAs retire
@@ -478,6 +493,8 @@ extern "C" int r4r_conv_pool_tc(const void* shadow, int64_t V, int Epad, int E, 
   {
     const char* e = getenv("R4R_CONV_LD");
     P.ld_ca = !(e && e[0] == 'c' && e[1] == 'g');
+    const char* d = getenv("R4R_CONV_DBG");
+    P.dbg = d ? atoi(d) : 0;
   }
   for (int h = 0; h < 2; ++h) { P.nb[h] = pl.nb[h]; P.f0[h] = pl.f0[h]; P.wofs[h] = pl.wofs[h]; }
 
