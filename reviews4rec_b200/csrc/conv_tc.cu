@@ -63,7 +63,7 @@ struct SharedCtl {
   unsigned long long empty[MAX_SLOTS];     // 1 arrival (multicast tcgen05.commit)
   unsigned long long tmem_full[2];         // 1 arrival (multicast tcgen05.commit)
   unsigned long long tmem_empty[2];        // leader's copy: 2 CTAs x NUM_EPI_WARPS arrivals
-  unsigned long long xchg_full[2];         // rank 0: one arrival per column thread of rank 1
+  unsigned long long xchg_full[2];         // rank 0: 1 arrival + Npad*8 transaction bytes stored by rank 1 (st.async)
   unsigned long long xchg_empty[2];        // rank 1: one arrival per column thread of rank 0
   uint32_t tmem_base;
   uint32_t pad;
@@ -93,8 +93,17 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
 }
+// Plain (CTA-scope release) arrive on a barrier of any CTA of the cluster.  Cluster-scope release /
+// acquire would be compiled to MEMBAR.GPU on the arrive and an L1 invalidation (CCTL.IVALL) on the
+// wait -- the latter throws away the L1-resident hot rows of the gather.  None of the data these
+// barriers guard is read through L1 by the waiting thread: operands go to the tensor cores through
+// the async proxy (ordered by fence.proxy.async before the arrive) and the DSMEM exchange uses
+// st.async + complete_tx.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
@@ -102,13 +111,15 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(addr), "r"(parity) : "memory");
   } while (!done);
 }
-__device__ __forceinline__ void st_cluster_u32(uint32_t cluster_addr, uint32_t v) {
-  asm volatile("st.shared::cluster.u32 [%0], %1;" :: "r"(cluster_addr), "r"(v) : "memory");
+// 4-byte store into another CTA's shared memory that signals completion (4 tx bytes) on a barrier there
+__device__ __forceinline__ void st_async_u32(uint32_t cluster_addr, uint32_t v, uint32_t cluster_bar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];"
+               :: "r"(cluster_addr), "r"(v), "r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -255,10 +266,11 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
       const uint32_t b = ndoc & 1u, use = ndoc >> 1;
       if (rank == 1) {
         mbar_wait(&ctl->xchg_empty[b], (use & 1u) ^ 1u);
-        st_cluster_u32(mapa(smem_u32(&ctl->xchg_val[b][f]), 0), __float_as_uint(v));
-        st_cluster_u32(mapa(smem_u32(&ctl->xchg_pos[b][f]), 0), (uint32_t)p);
-        mbar_arrive_cluster(mapa(smem_u32(&ctl->xchg_full[b]), 0));
+        const uint32_t rbar = mapa(smem_u32(&ctl->xchg_full[b]), 0);
+        st_async_u32(mapa(smem_u32(&ctl->xchg_val[b][f]), 0), __float_as_uint(v), rbar);
+        st_async_u32(mapa(smem_u32(&ctl->xchg_pos[b][f]), 0), (uint32_t)p, rbar);
       } else {
+        if (f == 0) mbar_arrive_expect_tx(&ctl->xchg_full[b], (uint32_t)P.Npad * 8u);
         mbar_wait(&ctl->xchg_full[b], use & 1u);
         const float ov = ctl->xchg_val[b][f];
         const int op = ctl->xchg_pos[b][f];
@@ -414,7 +426,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ctl->tmem_full[i], 1);
       mbar_init(&ctl->tmem_empty[i], 2 * NUM_EPI_WARPS);
-      mbar_init(&ctl->xchg_full[i], (uint32_t)P.Npad);
+      mbar_init(&ctl->xchg_full[i], 1);
       mbar_init(&ctl->xchg_empty[i], (uint32_t)P.Npad);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
