@@ -72,6 +72,10 @@ int r4r_conv_pool_tc(const void* shadow, int64_t V, int Epad, int E, int dtype,
                      const void* wpack, const float* conv_b, int F,
                      float* pooled, int32_t* argmax, void* stream);
 
+/* Diagnostics: when `buf32_u64` (device, 32 x uint64) is non-NULL every later r4r_conv_pool_tc launch
+ * writes the per-role cycle counters of its first CTA pair there (see conv_tc.cu); NULL turns it off. */
+int r4r_conv_debug_profile(void* buf32_u64);
+
 /* ---- a11: conv weight gradient through relu+max-pool (SURVEY.md finding 4) --------------------
  * dW[f,0,j,:] += sum_n gy[n,f] * Xpad[n, argmax[n,f]+j, :],  db[f] += sum_n gy[n,f]
  * with gy = gpooled * (pooled > 0).  Replaces autograd's convolution_backward + relu/max-pool

@@ -29,6 +29,7 @@ SIGNATURES = {
     "r4r_conv_wpack_bytes": (c_i64, [c_int, c_int]),
     "r4r_conv_pack_weights": (c_int, [c_vp, c_int, c_int, c_vp, c_int, c_vp]),
     "r4r_conv_pool_tc": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
+    "r4r_conv_debug_profile": (c_int, [c_vp]),
     "r4r_conv_wgrad_argmax": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
     "r4r_linear_fwd": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp]),
     "r4r_linear_bwd": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),

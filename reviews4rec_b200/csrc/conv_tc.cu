@@ -132,11 +132,15 @@ __device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void* src, uin
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
-// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (layout_type 0), version 1 (sm_100)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
+__device__ __forceinline__ uint64_t mk_desc(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+// UMMA shared-memory descriptor (K-major, SWIZZLE_NONE = layout_type 0, version 1 for sm_100):
+// bits 0-13 start address >> 4, 16-29 LBO >> 4, 32-45 SBO >> 4, bit 46 version.  mma_role() keeps
+// the two 32-bit halves and advances the address field by constants.
 // instruction descriptor: D=f32, A/B = f16 (0) or bf16 (1), both K-major, M=256 (pair), N=n
 __device__ __forceinline__ uint32_t umma_idesc(int fmt, int n) {
   return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)((2 * TILE_M) >> 4) << 24);
@@ -161,6 +165,18 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Diagnostics: time spent inside a barrier wait is added to a counter when profiling is on.
+#define TIMED_WAIT(acc, stmt)                         \
+  do {                                                \
+    if (prof_on) {                                    \
+      long long t0__ = clock64();                     \
+      stmt;                                           \
+      acc += clock64() - t0__;                        \
+    } else {                                          \
+      stmt;                                           \
+    }                                                 \
+  } while (0)
+
 struct Params {
   const uint8_t* shadow;     // [V][Epad] 2-byte elements
   long long row_bytes;       // Epad * 2
@@ -179,6 +195,8 @@ struct Params {
   int nslots;
   int cps;                   // chunks per ring slot (even)
   int slot_bytes;
+  unsigned long long* prof;  // diagnostics: per-role cycle counters of cluster 0 (r4r_conv_debug_profile), or NULL
+  int dbg;                   // diagnostics (R4R_CONV_DBG, results invalid): 1 no row shift, 2 no MMA, 4 no copies, 8 no epilogue compare
 };
 
 // ------------------------------------------------------------------------------------------
@@ -195,6 +213,8 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
   const uint32_t lane_base = (uint32_t)(q * 32) << 16;
   const uint32_t leader_tmem_empty[2] = {mapa(smem_u32(&ctl->tmem_empty[0]), 0), mapa(smem_u32(&ctl->tmem_empty[1]), 0)};
   uint32_t it = 0, ndoc = 0;
+  const bool prof_on = P.prof != nullptr && cluster_id == 0;
+  long long w_full = 0, w_bar = 0, w_xchg = 0, t_begin = clock64();
   for (long long doc = cluster_id; doc < P.N; doc += nclusters, ++ndoc) {
     // running maximum per filter column and the tile it came from (one byte per column, packed
     // four to a register)
@@ -206,7 +226,7 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
     for (int c = 0; c < EC / 4; ++c) btile[c] = 0u;
     for (int pt = 0; pt < npt; ++pt, ++it) {
       const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
-      mbar_wait(&ctl->tmem_full[buf], ph);
+      TIMED_WAIT(w_full, mbar_wait(&ctl->tmem_full[buf], ph));
       tc_fence_after();
       const bool valid = (pt * 2 * TILE_M + (int)rank * TILE_M + row) < npos;
       const uint32_t taddr = ctl->tmem_base + lane_base + buf * ACC_STRIDE + h * EC;
@@ -218,7 +238,7 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
         uint32_t v[8];
         tmem_ld8(taddr + c0, v);
         tmem_ld_wait();
-        if (valid) {
+        if (valid && !(P.dbg & 8)) {
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             float x = __uint_as_float(v[c]);
@@ -247,7 +267,7 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
       }
       if (lane == 0) { ctl->red_val[warp][c] = v; ctl->red_pos[warp][c] = p; }
     }
-    asm volatile("bar.sync %0, 128;" :: "r"(1 + h) : "memory");
+    TIMED_WAIT(w_bar, asm volatile("bar.sync %0, 128;" :: "r"(1 + h) : "memory"));
     const bool col_thread = row < EC;
     float v = -INFINITY;
     int p = 0x7fffffff;
@@ -265,13 +285,13 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
       const int f = h * EC + row;
       const uint32_t b = ndoc & 1u, use = ndoc >> 1;
       if (rank == 1) {
-        mbar_wait(&ctl->xchg_empty[b], (use & 1u) ^ 1u);
+        TIMED_WAIT(w_xchg, mbar_wait(&ctl->xchg_empty[b], (use & 1u) ^ 1u));
         const uint32_t rbar = mapa(smem_u32(&ctl->xchg_full[b]), 0);
         st_async_u32(mapa(smem_u32(&ctl->xchg_val[b][f]), 0), __float_as_uint(v), rbar);
         st_async_u32(mapa(smem_u32(&ctl->xchg_pos[b][f]), 0), (uint32_t)p, rbar);
       } else {
         if (f == 0) mbar_arrive_expect_tx(&ctl->xchg_full[b], (uint32_t)P.Npad * 8u);
-        mbar_wait(&ctl->xchg_full[b], use & 1u);
+        TIMED_WAIT(w_xchg, mbar_wait(&ctl->xchg_full[b], use & 1u));
         const float ov = ctl->xchg_val[b][f];
         const int op = ctl->xchg_pos[b][f];
         if (beats(ov, op, v, p)) { v = ov; p = op; }
@@ -283,6 +303,10 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
         }
       }
     }
+  }
+  if (prof_on && warp == 0 && lane == 0) {
+    unsigned long long* o = P.prof + rank * 16;
+    o[0] = (unsigned long long)(clock64() - t_begin); o[1] = w_full; o[2] = w_bar; o[3] = w_xchg;
   }
 }
 
@@ -318,6 +342,8 @@ __device__ __forceinline__ void producer_role(const Params& P, SharedCtl* ctl, u
     if (lane == 0) mbar_arrive_cluster(leader_full0 + (n % nslots) * 8u);
   };
 
+  const bool prof_on = P.prof != nullptr && cluster_id == 0;
+  long long w_empty = 0, w_group = 0, t_begin = clock64();
   uint32_t issued = 0, signalled = 0;
   long long doc = cluster_id;
   int pt = 0;
@@ -337,13 +363,13 @@ __device__ __forceinline__ void producer_role(const Params& P, SharedCtl* ctl, u
     }
     for (int s = 0; s < spt; ++s, ++issued) {
       const uint32_t slot = issued % nslots, round = issued / nslots;
-      mbar_wait(&ctl->empty[slot], (round & 1u) ^ 1u);
+      TIMED_WAIT(w_empty, mbar_wait(&ctl->empty[slot], (round & 1u) ^ 1u));
       const uint32_t dst = ring_base + slot * P.slot_bytes + dst_thread;
 #pragma unroll
       for (int m = 0; m < MAX_CPS / 8; ++m) {
         const int cl = c8 + 8 * m;                        // chunk within the slab
         const int ch = s * cps + cl;                      // chunk within the window row
-        if (cl < cps && ch < P.Kc) {
+        if (cl < cps && ch < P.Kc && !(P.dbg & 4)) {
 #pragma unroll
           for (int k = 0; k < ROWS_PER_THREAD; ++k) {
             if (r0 + 16 * k < TILE_M + 2) {
@@ -355,8 +381,7 @@ __device__ __forceinline__ void producer_role(const Params& P, SharedCtl* ctl, u
       }
       cp_async_commit();
       if (issued + 1 - signalled > (uint32_t)LAG) {
-        cp_async_wait<LAG>();
-        publish(signalled);
+        TIMED_WAIT(w_group, cp_async_wait<LAG>(); publish(signalled));
         ++signalled;
       }
     }
@@ -367,6 +392,10 @@ __device__ __forceinline__ void producer_role(const Params& P, SharedCtl* ctl, u
   }
   cp_async_wait<0>();
   for (; signalled < issued; ++signalled) publish(signalled);
+  if (prof_on && ptid == 0) {
+    unsigned long long* o = P.prof + rank * 16 + 4;
+    o[0] = (unsigned long long)(clock64() - t_begin); o[1] = w_empty; o[2] = w_group;
+  }
 }
 
 __device__ __forceinline__ void mma_role(const Params& P, SharedCtl* ctl, const uint8_t* bsm, const uint8_t* ring, int cluster_id,
@@ -378,26 +407,40 @@ __device__ __forceinline__ void mma_role(const Params& P, SharedCtl* ctl, const 
   const uint32_t a_base = smem_u32(ring), b_base = smem_u32(bsm);
   const uint32_t a_lbo = RA * 16, b_lbo = (uint32_t)(P.Npad / 2) * 16;
   const int nslots = P.nslots;
+  // low descriptor word = start address >> 4 | LBO >> 4 << 16, high word = SBO (128 B) >> 4 | version 1
+  const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+  const uint32_t a_step = a_lbo >> 4, b_step = b_lbo >> 4;      // one 16-byte K-chunk
+  const uint32_t a_j = (P.dbg & 1) ? 0u : 1u;                   // window row j: +16 bytes in the A slot
+  const uint32_t b_j = (uint32_t)P.Kc * b_step;                 //               +Kc chunks in the filter bank
+  const uint32_t a_lo0 = ((a_base >> 4) & 0x3FFFu) | (a_step << 16);
+  const uint32_t b_lo0 = ((b_base >> 4) & 0x3FFFu) | (b_step << 16);
+  const bool leader = elect_one();
   uint32_t consumed = 0, it = 0;
+  const bool prof_on = P.prof != nullptr && cluster_id == 0;
+  long long w_tmem = 0, w_full = 0, t_begin = clock64();
   for (long long doc = cluster_id; doc < P.N; doc += nclusters) {
     for (int pt = 0; pt < npt; ++pt, ++it) {
       const uint32_t buf = it & 1u, use = it >> 1;
-      mbar_wait(&ctl->tmem_empty[buf], (use & 1u) ^ 1u);       // both CTAs' epilogues drained this accumulator
+      TIMED_WAIT(w_tmem, mbar_wait(&ctl->tmem_empty[buf], (use & 1u) ^ 1u));       // both CTAs' epilogues drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = ctl->tmem_base + buf * ACC_STRIDE;
       for (int s = 0; s < spt; ++s, ++consumed) {
         const uint32_t slot = consumed % nslots, round = consumed / nslots;
-        mbar_wait(&ctl->full[slot], round & 1u);               // both CTAs' producers published this slab
+        TIMED_WAIT(w_full, mbar_wait(&ctl->full[slot], round & 1u));               // both CTAs' producers published this slab
         tc_fence_after();
-        if (lane == 0) {
+        if (leader) {
+          // descriptors advance by constants: +2 K-chunks per K=16 step, +1 row (16 B) per window row j
           const int nk = min(cps, P.Kc - s * cps) >> 1;        // K=16 steps in this slab
+          uint32_t a_lo = a_lo0 + ((slot * (uint32_t)P.slot_bytes) >> 4);
+          uint32_t b_lo = b_lo0 + (uint32_t)(s * cps) * b_step;
+          uint32_t acc = s ? 1u : 0u;
           for (int kk = 0; kk < nk; ++kk) {
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              uint64_t ad = umma_desc(a_base + slot * P.slot_bytes + (uint32_t)(2 * kk) * a_lbo + j * 16, a_lbo, 128);
-              uint64_t bd = umma_desc(b_base + (uint32_t)(j * P.Kc + s * cps + 2 * kk) * b_lbo, b_lbo, 128);
-              umma_f16_pair(d_tmem, ad, bd, idesc, (s | kk | j) ? 1u : 0u);
-            }
+            umma_f16_pair(d_tmem, mk_desc(a_lo, desc_hi), mk_desc(b_lo, desc_hi), idesc, acc);
+            umma_f16_pair(d_tmem, mk_desc(a_lo + a_j, desc_hi), mk_desc(b_lo + b_j, desc_hi), idesc, 1u);
+            umma_f16_pair(d_tmem, mk_desc(a_lo + 2 * a_j, desc_hi), mk_desc(b_lo + 2 * b_j, desc_hi), idesc, 1u);
+            acc = 1u;
+            a_lo += 2 * a_step;
+            b_lo += 2 * b_step;
           }
           umma_commit_pair(&ctl->empty[slot]);                      // slot reusable (both CTAs) once these MMAs retire
           if (s == spt - 1) umma_commit_pair(&ctl->tmem_full[buf]); // accumulator complete (both CTAs)
@@ -405,6 +448,10 @@ __device__ __forceinline__ void mma_role(const Params& P, SharedCtl* ctl, const 
         __syncwarp();
       }
     }
+  }
+  if (prof_on && leader) {
+    unsigned long long* o = P.prof + 8;
+    o[0] = (unsigned long long)(clock64() - t_begin); o[1] = w_tmem; o[2] = w_full;
   }
 }
 
@@ -511,6 +558,15 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
 }
 }  // namespace
 
+static unsigned long long* g_prof = nullptr;
+// Diagnostics: 32 x uint64 device buffer receiving the per-role cycle counters of cluster 0
+// ([rank*16+0..3] epilogue total / wait tmem_full / bar.sync / exchange, [rank*16+4..6] producer
+// total / wait empty / wait copies, [8..10] MMA total / wait tmem_empty / wait full); NULL = off.
+extern "C" int r4r_conv_debug_profile(void* buf32_u64) {
+  g_prof = static_cast<unsigned long long*>(buf32_u64);
+  return 0;
+}
+
 extern "C" int64_t r4r_conv_wpack_bytes(int E, int F) {
   PackPlan pl;
   if (!make_plan(E, F, pl)) return -1;
@@ -587,6 +643,11 @@ extern "C" int r4r_conv_pool_tc(const void* shadow, int64_t V, int Epad, int E, 
   P.wpack = static_cast<const uint8_t*>(wpack);
   P.bias = conv_b; P.pooled = pooled; P.argmax = argmax;
   P.fmt = dtype; P.nslots = nslots; P.cps = cps; P.slot_bytes = slot_bytes;
+  {
+    const char* d = getenv("R4R_CONV_DBG");
+    P.dbg = d ? atoi(d) : 0;
+  }
+  P.prof = g_prof;
 
   R4R_CUDA(cudaFuncSetAttribute(conv_pool_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   long long nclusters = sm_count / 2;

@@ -48,3 +48,16 @@ fl = 2.0 * (a.T + 2) * 100 * 3 * a.E * a.docs
 print("conv_bench dist=%s docs=%d mode=%s env=%s: %.3f ms/launch  %.1f TFLOP/s  %.0f docs/s  alg %.0f GB/s" % (
     a.dist, a.docs, a.mode, {k: v for k, v in os.environ.items() if k.startswith("R4R_")}, ms, fl / ms / 1e9,
     a.docs / ms * 1e3, a.docs * a.T * (8 + 4 * a.E) / ms / 1e6))
+if os.environ.get("CONV_PROF"):
+    from reviews4rec_b200 import _lib
+    import ctypes
+    buf = torch.zeros(32, dtype=torch.int64, device="cuda")
+    _lib.lib.r4r_conv_debug_profile(ctypes.c_void_p(buf.data_ptr()))
+    ops.conv_pool_forward(pool[0], table, w, b, a.mode, sh)
+    torch.cuda.synchronize()
+    _lib.lib.r4r_conv_debug_profile(ctypes.c_void_p(0))
+    v = buf.tolist()
+    for r in (0, 1):
+        print("rank%d epilogue: total %d  wait_tmem_full %d  bar %d  xchg %d" % (r, *v[r * 16: r * 16 + 4]))
+        print("rank%d producer: total %d  wait_empty %d  wait_copies+publish %d" % (r, *v[r * 16 + 4: r * 16 + 7]))
+    print("mma: total %d  wait_tmem_empty %d  wait_full %d" % tuple(v[8:11]))
