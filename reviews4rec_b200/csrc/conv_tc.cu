@@ -196,16 +196,66 @@ struct Params {
   int cps;                   // chunks per ring slot (even)
   int slot_bytes;
   unsigned long long* prof;  // diagnostics: per-role cycle counters of cluster 0 (r4r_conv_debug_profile), or NULL
-  int dbg;                   // diagnostics (R4R_CONV_DBG, results invalid): 1 no row shift, 2 no MMA, 4 no copies, 8 no epilogue compare
 };
 
 // ------------------------------------------------------------------------------------------
 // does (ov, op) beat (v, p)?  larger value, then smaller position
 __device__ __forceinline__ bool beats(float ov, int op, float v, int p) { return ov > v || (ov == v && op < p); }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
+}
+
+__host__ __device__ constexpr int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+// Warp-wide (max value, smallest key) reduction of N columns held by every lane, as a transposing
+// butterfly: in the round with lane distance O each lane keeps one half of its columns and trades
+// the other half with its partner, so the column count halves per round and the whole reduction
+// costs ~N shuffle pairs instead of 5*N.  Column bit log2(N)-1-r ends up equal to lane bit 4-r.
+template <int N, int O>
+struct Butterfly {
+  static __device__ __forceinline__ void run(float (&v)[N], uint32_t (&key)[N], int lane) {
+    if constexpr (O > 0) {
+      const bool up = (lane & O) != 0;
+      if constexpr (N > 1) {
+        constexpr int H = N / 2;
+        float nv[H];
+        uint32_t nk[H];
+#pragma unroll
+        for (int c = 0; c < H; ++c) {
+          float mine = up ? v[c + H] : v[c];
+          uint32_t mk = up ? key[c + H] : key[c];
+          const float send = up ? v[c] : v[c + H];
+          const uint32_t sk = up ? key[c] : key[c + H];
+          const float rv = __shfl_xor_sync(0xffffffffu, send, O);
+          const uint32_t rk = __shfl_xor_sync(0xffffffffu, sk, O);
+          if (rv > mine || (rv == mine && rk < mk)) { mine = rv; mk = rk; }
+          nv[c] = mine;
+          nk[c] = mk;
+        }
+        Butterfly<H, O / 2>::run(nv, nk, lane);
+#pragma unroll
+        for (int c = 0; c < H; ++c) { v[c] = nv[c]; key[c] = nk[c]; }
+      } else {
+        const float rv = __shfl_xor_sync(0xffffffffu, v[0], O);
+        const uint32_t rk = __shfl_xor_sync(0xffffffffu, key[0], O);
+        if (rv > v[0] || (rv == v[0] && rk < key[0])) { v[0] = rv; key[0] = rk; }
+        Butterfly<1, O / 2>::run(v, key, lane);
+      }
+    }
+  }
+};
+
 template <int EC>   // accumulator columns handled by one epilogue warp = Npad / 2
 __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, uint32_t rank, int cluster_id, int nclusters,
                                               int warp, int lane) {
+  constexpr int P2 = next_pow2(EC);
+  constexpr int KEEP = P2 >= 32 ? P2 / 32 : 1;           // columns per lane after the butterfly
+  constexpr int SHIFT = P2 >= 32 ? 0 : (P2 == 16 ? 1 : 2); // lanes sharing one column: 1 << SHIFT
   const int npos = P.T + 2;
   const int npt = (npos + 2 * TILE_M - 1) / (2 * TILE_M);
   const int q = warp & 3, h = warp >> 2;
@@ -218,12 +268,12 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
   for (long long doc = cluster_id; doc < P.N; doc += nclusters, ++ndoc) {
     // running maximum per filter column and the tile it came from (one byte per column, packed
     // four to a register)
-    float best[EC];
-    uint32_t btile[EC / 4];
+    float best[P2];
+    uint32_t btile[P2 / 4];
 #pragma unroll
-    for (int c = 0; c < EC; ++c) best[c] = -INFINITY;
+    for (int c = 0; c < P2; ++c) best[c] = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < EC / 4; ++c) btile[c] = 0u;
+    for (int c = 0; c < P2 / 4; ++c) btile[c] = 0u;
     for (int pt = 0; pt < npt; ++pt, ++it) {
       const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
       TIMED_WAIT(w_full, mbar_wait(&ctl->tmem_full[buf], ph));
@@ -234,17 +284,26 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
 #pragma unroll
       for (int k = 0; k < 4; ++k) tsh[k] = (uint32_t)pt << (8 * k);
 #pragma unroll
-      for (int c0 = 0; c0 < EC; c0 += 8) {
-        uint32_t v[8];
-        tmem_ld8(taddr + c0, v);
-        tmem_ld_wait();
-        if (valid && !(P.dbg & 8)) {
+      for (int c0 = 0; c0 < EC; c0 += 16) {
+        uint32_t v[16];
+        if (c0 + 16 <= EC) {
+          tmem_ld16(taddr + c0, v);
+        } else {
+          uint32_t v8[8];
+          tmem_ld8(taddr + c0, v8);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float x = __uint_as_float(v[c]);
-            if (x > best[c0 + c]) {
-              best[c0 + c] = x;
-              btile[(c0 + c) >> 2] = (btile[(c0 + c) >> 2] & ~(0xffu << (8 * (c & 3)))) | tsh[c & 3];
+          for (int c = 0; c < 8; ++c) v[c] = v8[c];
+        }
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            if (c0 + c < EC) {
+              float x = __uint_as_float(v[c]);
+              if (x > best[c0 + c]) {
+                best[c0 + c] = x;
+                btile[(c0 + c) >> 2] = (btile[(c0 + c) >> 2] & ~(0xffu << (8 * (c & 3)))) | tsh[c & 3];
+              }
             }
           }
         }
@@ -253,19 +312,25 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(leader_tmem_empty[buf]);
     }
-    // ---- per-document reduction over this CTA's 128 rows: max value, smallest position on ties
+    // ---- per-document reduction over the warp's 32 rows: max value, smallest position on ties.
+    // key = tile << 5 | lane orders positions within the warp (same CTA rank and lane quarter).
+    {
+      uint32_t key[P2];
 #pragma unroll
-    for (int c = 0; c < EC; ++c) {
-      float v = best[c];
-      int p = v == -INFINITY ? 0x7fffffff
-                             : (int)((btile[c >> 2] >> (8 * (c & 3))) & 0xffu) * 2 * TILE_M + (int)rank * TILE_M + row;
+      for (int c = 0; c < P2; ++c) key[c] = (((btile[c >> 2] >> (8 * (c & 3))) & 0xffu) << 5) | (uint32_t)lane;
+      Butterfly<P2, 16>::run(best, key, lane);
+      if ((lane & ((1 << SHIFT) - 1)) == 0) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        float ov = __shfl_xor_sync(0xffffffffu, v, o);
-        int op = __shfl_xor_sync(0xffffffffu, p, o);
-        if (beats(ov, op, v, p)) { v = ov; p = op; }
+        for (int i = 0; i < KEEP; ++i) {
+          const int c = P2 >= 32 ? lane * KEEP + i : lane >> SHIFT;
+          if (c < EC) {
+            const float v = best[i];
+            ctl->red_val[warp][c] = v;
+            ctl->red_pos[warp][c] = v == -INFINITY ? 0x7fffffff
+                                                   : (int)(key[i] >> 5) * 2 * TILE_M + (int)rank * TILE_M + q * 32 + (int)(key[i] & 31u);
+          }
+        }
       }
-      if (lane == 0) { ctl->red_val[warp][c] = v; ctl->red_pos[warp][c] = p; }
     }
     TIMED_WAIT(w_bar, asm volatile("bar.sync %0, 128;" :: "r"(1 + h) : "memory"));
     const bool col_thread = row < EC;
@@ -321,6 +386,7 @@ __device__ __forceinline__ void producer_role(const Params& P, SharedCtl* ctl, u
   const uint32_t dst_thread = (uint32_t)(c8 * RA * 16 + r0 * 16);
   const int nslots = P.nslots;
   const uint32_t leader_full0 = mapa(smem_u32(&ctl->full[0]), 0);
+  const bool last_row = r0 + 16 * (ROWS_PER_THREAD - 1) < TILE_M + 2;   // rows 128, 129 exist for r0 < 2 only
 
   // Token ids of a tile's rows are fetched ONE TILE AHEAD into registers (unchecked, so the nine
   // loads are issued back to back and their HBM latency hides behind the current tile's slabs);
@@ -354,12 +420,15 @@ __device__ __forceinline__ void producer_role(const Params& P, SharedCtl* ctl, u
     int pt_next = pt + 1;
     if (pt_next == npt) { pt_next = 0; ndoc += nclusters; }
     if (ndoc < P.N) fetch(ndoc, pt_next, nxt);
+    // per row: source pointer (any valid address for a zero row) and a mask of the zero rows
     const uint8_t* src[ROWS_PER_THREAD];
+    uint32_t zmask = 0u;
 #pragma unroll
     for (int k = 0; k < ROWS_PER_THREAD; ++k) {
       const long long tok = cur[k];
       if (tok < -1 || tok >= P.V) __trap();               // the reference device-asserts on OOB ids
-      src[k] = tok < 0 ? nullptr : P.shadow + tok * P.row_bytes;
+      src[k] = P.shadow + (tok < 0 ? 0 : tok) * P.row_bytes;
+      zmask |= tok < 0 ? (1u << k) : 0u;
     }
     for (int s = 0; s < spt; ++s, ++issued) {
       const uint32_t slot = issued % nslots, round = issued / nslots;
@@ -369,14 +438,14 @@ __device__ __forceinline__ void producer_role(const Params& P, SharedCtl* ctl, u
       for (int m = 0; m < MAX_CPS / 8; ++m) {
         const int cl = c8 + 8 * m;                        // chunk within the slab
         const int ch = s * cps + cl;                      // chunk within the window row
-        if (cl < cps && ch < P.Kc && !(P.dbg & 4)) {
+        if (cl < cps && ch < P.Kc) {
+          const uint32_t d = dst + m * (8 * RA * 16);
+          const int off = ch * 16;
 #pragma unroll
-          for (int k = 0; k < ROWS_PER_THREAD; ++k) {
-            if (r0 + 16 * k < TILE_M + 2) {
-              const uint8_t* sp = src[k];
-              cp_async16_ca(dst + m * (8 * RA * 16) + k * 256, sp ? sp + ch * 16 : P.shadow, sp ? 16u : 0u);
-            }
-          }
+          for (int k = 0; k < ROWS_PER_THREAD - 1; ++k)
+            cp_async16_ca(d + k * 256, src[k] + off, (zmask >> k) & 1u ? 0u : 16u);
+          if (last_row) cp_async16_ca(d + (ROWS_PER_THREAD - 1) * 256, src[ROWS_PER_THREAD - 1] + off,
+                                      (zmask >> (ROWS_PER_THREAD - 1)) & 1u ? 0u : 16u);
         }
       }
       cp_async_commit();
@@ -410,7 +479,7 @@ __device__ __forceinline__ void mma_role(const Params& P, SharedCtl* ctl, const 
   // low descriptor word = start address >> 4 | LBO >> 4 << 16, high word = SBO (128 B) >> 4 | version 1
   const uint32_t desc_hi = (128u >> 4) | (1u << 14);
   const uint32_t a_step = a_lbo >> 4, b_step = b_lbo >> 4;      // one 16-byte K-chunk
-  const uint32_t a_j = (P.dbg & 1) ? 0u : 1u;                   // window row j: +16 bytes in the A slot
+  const uint32_t a_j = 1u;                   // window row j: +16 bytes in the A slot
   const uint32_t b_j = (uint32_t)P.Kc * b_step;                 //               +Kc chunks in the filter bank
   const uint32_t a_lo0 = ((a_base >> 4) & 0x3FFFu) | (a_step << 16);
   const uint32_t b_lo0 = ((b_base >> 4) & 0x3FFFu) | (b_step << 16);
@@ -643,10 +712,6 @@ extern "C" int r4r_conv_pool_tc(const void* shadow, int64_t V, int Epad, int E, 
   P.wpack = static_cast<const uint8_t*>(wpack);
   P.bias = conv_b; P.pooled = pooled; P.argmax = argmax;
   P.fmt = dtype; P.nslots = nslots; P.cps = cps; P.slot_bytes = slot_bytes;
-  {
-    const char* d = getenv("R4R_CONV_DBG");
-    P.dbg = d ? atoi(d) : 0;
-  }
   P.prof = g_prof;
 
   R4R_CUDA(cudaFuncSetAttribute(conv_pool_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
