@@ -1,0 +1,272 @@
+// shard.cu -- K8: device side of the row-sharded table lookups.
+//
+// The reference is single-process (no NCCL / torch.distributed call anywhere), so the
+// semantics these kernels keep are simply those of nn.Embedding / Tensor.gather over the FULL table
+// (DeepCoNN.py:53-54,70-71, NARRE.py:87-88,110-116, TransNet.py:108-109, MF.py:45-46,52-53) when row
+// r of the table lives on rank r % P at local row r / P.
+//
+// A lookup is   plan -> [ids out] -> serve -> [rows back] -> remap/gather   where the two bracketed
+// steps are either NCCL all-to-alls (equal splits, CUDA-graph capturable) or -- fused variant --
+// r4r_shard_serve_p2p, which gathers the requested rows and stores them straight into the
+// requesters' receive buffers over NVLink peer mappings.
+//
+// Message layout (int64 words): for every destination / source rank q a block of 1+cap words,
+//   msg[q*(1+cap)]       = number of valid rows n_q
+//   msg[q*(1+cap)+1+j]   = local row index at the owner, j < n_q
+// Row payloads are laid out [q][cap][row_bytes]; the row requested as (q, j) comes back at slot
+// q*cap + j, which is what `slot[]` / `pos[]` hold.
+#include "common.cuh"
+
+namespace {
+constexpr int THREADS = 256;
+
+// ---- word-table plan, step 1: presence flags of the token ids of this rank's documents
+__global__ void __launch_bounds__(THREADS) shard_mark_kernel(const int64_t* __restrict__ idx, int64_t n, int64_t V,
+                                                             int32_t* __restrict__ flags) {
+  for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS) {
+    const int64_t id = __ldg(idx + i);
+    if (id < 0 || id >= V) __trap();                  // the reference device-asserts on OOB ids
+    if (flags[id] == 0) flags[id] = 1;                // benign race: every writer stores the same value
+  }
+}
+
+// ---- word-table plan, step 2: CTA o compacts the flagged rows owned by rank o (ids o, o+P, ...)
+// into its request block, in increasing id order (deterministic), and records each id's slot.
+constexpr int PLAN_THREADS = 1024;
+__global__ void __launch_bounds__(PLAN_THREADS) shard_plan_kernel(int32_t* __restrict__ flags, int64_t V, int P, int64_t cap,
+                                                                  int64_t* __restrict__ req, int64_t* __restrict__ slot) {
+  __shared__ int warp_tot[PLAN_THREADS / 32];
+  __shared__ int chunk_base;
+  const int o = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t rows = (V - o + P - 1) / P;            // rows owned by rank o
+  int64_t* block = req + (int64_t)o * (1 + cap);
+  if (threadIdx.x == 0) chunk_base = 0;
+  __syncthreads();
+  for (int64_t l0 = 0; l0 < rows; l0 += PLAN_THREADS) {
+    const int64_t l = l0 + threadIdx.x;
+    const int64_t id = l * P + o;
+    const bool on = l < rows && flags[id] != 0;
+    const unsigned ballot = __ballot_sync(0xffffffffu, on);
+    const int before = __popc(ballot & ((1u << lane) - 1u));
+    if (lane == 0) warp_tot[warp] = __popc(ballot);
+    __syncthreads();
+    int wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += warp_tot[w];
+    const int base = chunk_base;
+    if (l < rows) {
+      if (on) {
+        const int64_t p = base + wbase + before;
+        block[1 + p] = l;
+        slot[id] = (int64_t)o * cap + p;
+        flags[id] = 0;                                // leave the flag array clean for the next step
+      } else {
+        slot[id] = -1;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == PLAN_THREADS - 1) chunk_base = base + wbase + __popc(ballot);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) block[0] = chunk_base;
+}
+
+// ---- id-table plan: no de-duplication (n is a few rows per rating); pos[i] = slot of ids[i]
+__global__ void __launch_bounds__(THREADS) shard_bucket_kernel(const int64_t* __restrict__ ids, int64_t n, int64_t R, int P,
+                                                               int64_t cap, int64_t* __restrict__ req, int64_t* __restrict__ pos) {
+  for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS) {
+    const int64_t id = __ldg(ids + i);
+    if (id < 0 || id >= R) __trap();
+    const int o = (int)(id % P);
+    int64_t* block = req + (int64_t)o * (1 + cap);
+    const unsigned long long k = atomicAdd(reinterpret_cast<unsigned long long*>(block), 1ULL);
+    block[1 + k] = id / P;
+    pos[i] = (int64_t)o * cap + (int64_t)k;
+  }
+}
+
+// ---- owner side: copy the requested rows of the local shard into per-requester payload blocks.
+// One warp per (requester, j) row, 16-byte lanes when the row allows it.  `out_ptrs[q]` is where
+// requester q's block [cap][row_bytes] starts: a local staging buffer (NCCL path) or requester q's
+// receive buffer mapped over NVLink (fused path: the gather IS the all-to-all).
+struct ServeArgs {
+  uint8_t* out[16];
+};
+
+template <bool VEC16>
+__global__ void __launch_bounds__(THREADS) shard_serve_kernel(const uint8_t* __restrict__ shard, int64_t rows_local, int row_bytes,
+                                                              const int64_t* __restrict__ rreq, int P, int64_t cap,
+                                                              const __grid_constant__ ServeArgs A) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (THREADS / 32);
+  const int64_t total = (int64_t)P * cap;
+  for (int64_t w = (int64_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5); w < total; w += warps) {
+    const int q = (int)(w / cap);
+    const int64_t j = w - (int64_t)q * cap;
+    const int64_t* block = rreq + (int64_t)q * (1 + cap);
+    const int64_t nq = __ldg(block);
+    if (nq < 0 || nq > cap) __trap();
+    if (j >= nq) continue;
+    const int64_t row = __ldg(block + 1 + j);
+    if (row < 0 || row >= rows_local) __trap();
+    const uint8_t* src = shard + row * (int64_t)row_bytes;
+    uint8_t* dst = A.out[q] + j * (int64_t)row_bytes;
+    if (VEC16) {
+      const uint4* s4 = reinterpret_cast<const uint4*>(src);
+      uint4* d4 = reinterpret_cast<uint4*>(dst);
+      for (int c = lane; c < row_bytes / 16; c += 32) d4[c] = __ldg(s4 + c);
+    } else {
+      const uint32_t* s1 = reinterpret_cast<const uint32_t*>(src);
+      uint32_t* d1 = reinterpret_cast<uint32_t*>(dst);
+      for (int c = lane; c < row_bytes / 4; c += 32) d1[c] = __ldg(s1 + c);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(THREADS) shard_remap_kernel(const int64_t* __restrict__ idx, int64_t n, const int64_t* __restrict__ slot,
+                                                              int64_t V, int64_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS) {
+    const int64_t id = __ldg(idx + i);
+    if (id < 0 || id >= V) __trap();
+    const int64_t s = __ldg(slot + id);
+    if (s < 0) __trap();                               // id was not part of the plan
+    out[i] = s;
+  }
+}
+
+// ---- owner side of the backward: gtable[row(q,j), :] += grads[q*cap + j, :] for the valid (q, j).
+// Same warp-segmented combining as r4r_rows_scatter_add (one atomic per distinct row per warp).
+__global__ void __launch_bounds__(THREADS) shard_scatter_add_kernel(const float* __restrict__ grads, const int64_t* __restrict__ rreq,
+                                                                    int P, int64_t cap, int L, float* __restrict__ gtable,
+                                                                    int64_t rows_local, float scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t total = (int64_t)P * cap;
+  const int64_t stride = (int64_t)gridDim.x * THREADS;
+  for (int64_t i0 = (int64_t)blockIdx.x * THREADS + (threadIdx.x & ~31); i0 < total; i0 += stride) {
+    const int64_t i = i0 + lane;
+    bool valid = i < total;
+    int64_t row = -1 - lane;                           // distinct negatives never match
+    if (valid) {
+      const int q = (int)(i / cap);
+      const int64_t j = i - (int64_t)q * cap;
+      const int64_t* block = rreq + (int64_t)q * (1 + cap);
+      valid = j < __ldg(block);
+      if (valid) {
+        row = __ldg(block + 1 + j);
+        if (row < 0 || row >= rows_local) __trap();
+      }
+    }
+    if (__ballot_sync(0xffffffffu, valid) == 0u) continue;
+    const unsigned grp = __match_any_sync(0xffffffffu, row);
+    const int leader = __ffs(grp) - 1;
+    for (int c = 0; c < L; ++c) {
+      const float g = valid ? __ldg(grads + i * (int64_t)L + c) : 0.0f;
+      float s = 0.0f;
+      unsigned rem = grp;
+      while (rem) {
+        const int src = __ffs(rem) - 1;
+        s += __shfl_sync(grp, g, src);
+        rem &= rem - 1;
+      }
+      if (valid && lane == leader) atomicAdd(gtable + row * (int64_t)L + c, s * scale);
+    }
+  }
+}
+
+inline unsigned grid_of(int64_t items, int per_block, int cap_blocks = 148 * 8) {
+  int64_t b = cdiv64(items, per_block);
+  if (b < 1) b = 1;
+  if (b > cap_blocks) b = cap_blocks;
+  return (unsigned)b;
+}
+}  // namespace
+
+extern "C" int r4r_shard_mark(const int64_t* idx, int64_t n, int64_t V, int32_t* flags, void* stream) {
+  R4R_REQUIRE(idx && flags, R4R_EINVAL, "shard_mark: null pointer");
+  R4R_REQUIRE(n >= 0 && V > 0, R4R_EINVAL, "shard_mark: bad sizes");
+  if (n == 0) return 0;
+  shard_mark_kernel<<<grid_of(n, THREADS * 4), THREADS, 0, as_stream(stream)>>>(idx, n, V, flags);
+  R4R_CHECK_LAUNCH("shard_mark");
+  return 0;
+}
+
+extern "C" int r4r_shard_plan(int32_t* flags, int64_t V, int P, int64_t cap, int64_t* req, int64_t* slot, void* stream) {
+  R4R_REQUIRE(flags && req && slot, R4R_EINVAL, "shard_plan: null pointer");
+  R4R_REQUIRE(V > 0 && P >= 1 && P <= 16 && cap >= (V + P - 1) / P, R4R_EINVAL,
+              "shard_plan: need 1 <= P <= 16 and cap >= ceil(V/P) (V=%lld P=%d cap=%lld)", (long long)V, P, (long long)cap);
+  shard_plan_kernel<<<P, PLAN_THREADS, 0, as_stream(stream)>>>(flags, V, P, cap, req, slot);
+  R4R_CHECK_LAUNCH("shard_plan");
+  return 0;
+}
+
+extern "C" int r4r_shard_bucket(const int64_t* ids, int64_t n, int64_t R, int P, int64_t cap, int64_t* req, int64_t* pos,
+                                void* stream) {
+  R4R_REQUIRE(ids && req && pos, R4R_EINVAL, "shard_bucket: null pointer");
+  R4R_REQUIRE(n >= 0 && R > 0 && P >= 1 && P <= 16 && cap >= n, R4R_EINVAL,
+              "shard_bucket: need 1 <= P <= 16 and cap >= n (n=%lld cap=%lld)", (long long)n, (long long)cap);
+  R4R_CUDA(cudaMemsetAsync(req, 0, (size_t)P * (size_t)(1 + cap) * sizeof(int64_t), as_stream(stream)));
+  if (n == 0) return 0;
+  shard_bucket_kernel<<<grid_of(n, THREADS), THREADS, 0, as_stream(stream)>>>(ids, n, R, P, cap, req, pos);
+  R4R_CHECK_LAUNCH("shard_bucket");
+  return 0;
+}
+
+static int serve_launch(const void* shard, int64_t rows_local, int row_bytes, const int64_t* rreq, int P, int64_t cap,
+                        const ServeArgs& A, bool aligned, void* stream) {
+  const int64_t total = (int64_t)P * cap;
+  const unsigned grid = grid_of(total, THREADS / 32, 148 * 16);
+  const uint8_t* s = static_cast<const uint8_t*>(shard);
+  if (aligned && row_bytes % 16 == 0)
+    shard_serve_kernel<true><<<grid, THREADS, 0, as_stream(stream)>>>(s, rows_local, row_bytes, rreq, P, cap, A);
+  else
+    shard_serve_kernel<false><<<grid, THREADS, 0, as_stream(stream)>>>(s, rows_local, row_bytes, rreq, P, cap, A);
+  R4R_CHECK_LAUNCH("shard_serve");
+  return 0;
+}
+
+extern "C" int r4r_shard_serve(const void* shard, int64_t rows_local, int row_bytes, const int64_t* rreq, int P, int64_t cap,
+                               void* out, void* stream) {
+  R4R_REQUIRE(shard && rreq && out, R4R_EINVAL, "shard_serve: null pointer");
+  R4R_REQUIRE(rows_local > 0 && row_bytes > 0 && row_bytes % 4 == 0 && P >= 1 && P <= 16 && cap > 0, R4R_EINVAL,
+              "shard_serve: bad sizes (row_bytes=%d must be a multiple of 4, 1 <= P <= 16)", row_bytes);
+  ServeArgs A;
+  for (int q = 0; q < 16; ++q) A.out[q] = q < P ? static_cast<uint8_t*>(out) + (size_t)q * (size_t)cap * (size_t)row_bytes : nullptr;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(shard) | reinterpret_cast<uintptr_t>(out)) % 16) == 0;
+  return serve_launch(shard, rows_local, row_bytes, rreq, P, cap, A, aligned, stream);
+}
+
+extern "C" int r4r_shard_serve_p2p(const void* shard, int64_t rows_local, int row_bytes, const int64_t* rreq, int P, int64_t cap,
+                                   void* const* out_ptrs_host, void* stream) {
+  R4R_REQUIRE(shard && rreq && out_ptrs_host, R4R_EINVAL, "shard_serve_p2p: null pointer");
+  R4R_REQUIRE(rows_local > 0 && row_bytes > 0 && row_bytes % 4 == 0 && P >= 1 && P <= 16 && cap > 0, R4R_EINVAL,
+              "shard_serve_p2p: bad sizes (row_bytes=%d must be a multiple of 4, 1 <= P <= 16)", row_bytes);
+  ServeArgs A;
+  uintptr_t bits = reinterpret_cast<uintptr_t>(shard);
+  for (int q = 0; q < 16; ++q) {
+    A.out[q] = q < P ? static_cast<uint8_t*>(out_ptrs_host[q]) : nullptr;
+    if (q < P) {
+      R4R_REQUIRE(A.out[q], R4R_EINVAL, "shard_serve_p2p: null receive pointer for rank %d", q);
+      bits |= reinterpret_cast<uintptr_t>(A.out[q]);
+    }
+  }
+  return serve_launch(shard, rows_local, row_bytes, rreq, P, cap, A, bits % 16 == 0, stream);
+}
+
+extern "C" int r4r_shard_remap(const int64_t* idx, int64_t n, const int64_t* slot, int64_t V, int64_t* out, void* stream) {
+  R4R_REQUIRE(idx && slot && out, R4R_EINVAL, "shard_remap: null pointer");
+  R4R_REQUIRE(n >= 0 && V > 0, R4R_EINVAL, "shard_remap: bad sizes");
+  if (n == 0) return 0;
+  shard_remap_kernel<<<grid_of(n, THREADS * 4), THREADS, 0, as_stream(stream)>>>(idx, n, slot, V, out);
+  R4R_CHECK_LAUNCH("shard_remap");
+  return 0;
+}
+
+extern "C" int r4r_shard_scatter_add(const float* grads, const int64_t* rreq, int P, int64_t cap, int L, float* gtable,
+                                     int64_t rows_local, float scale, void* stream) {
+  R4R_REQUIRE(grads && rreq && gtable, R4R_EINVAL, "shard_scatter_add: null pointer");
+  R4R_REQUIRE(P >= 1 && P <= 16 && cap > 0 && L > 0 && rows_local > 0, R4R_EINVAL, "shard_scatter_add: bad sizes");
+  shard_scatter_add_kernel<<<grid_of((int64_t)P * cap, THREADS), THREADS, 0, as_stream(stream)>>>(grads, rreq, P, cap, L, gtable,
+                                                                                                 rows_local, scale);
+  R4R_CHECK_LAUNCH("shard_scatter_add");
+  return 0;
+}
