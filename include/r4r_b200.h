@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define R4R_ABI_VERSION 1
+#define R4R_ABI_VERSION 2
 
 #define R4R_EINVAL   (-1)   /* bad argument (null pointer, size out of supported range)          */
 #define R4R_EUNSUP   (-2)   /* shape outside what the sm_100a kernels were built for             */
@@ -47,7 +47,8 @@ int r4r_word_gather_f32(const float* table, int64_t V, int E, const int64_t* idx
                         float* out, void* stream);
 
 /* Private reduced-precision copy of the frozen word table (SURVEY.md finding 2):
- * shadow[v, 0:E] = cvt(table[v,:]), shadow[v, E:Epad] = 0.  Epad % 8 == 0, row stride = Epad. */
+ * shadow[v, 0:E] = cvt(table[v,:]), shadow[v, E:Epad] = 0.  Epad % 8 == 0, row stride = Epad.
+ * `shadow` holds V+1 rows: row V is all zero (r4r_conv_pool_tc reads the conv's zero padding from it). */
 int r4r_shadow_build(const float* table, int64_t V, int E, void* shadow, int Epad, int dtype,
                      void* stream);
 
@@ -70,7 +71,19 @@ int r4r_conv_pack_weights(const float* conv_w, int E, int F, void* wpack, int dt
 int r4r_conv_pool_tc(const void* shadow, int64_t V, int Epad, int E, int dtype,
                      const int64_t* idx, int64_t N, int T,
                      const void* wpack, const float* conv_b, int F,
-                     float* pooled, int32_t* argmax, void* stream);
+                     float* pooled, int32_t* argmax,
+                     const int32_t* doc_len, const int32_t* doc_order, void* stream);
+
+/* Work plan for r4r_conv_pool_tc (optional: pass NULL, NULL to process every row of every document).
+ * The readers pad documents to T with one repeated token that is embedded like any other
+ * (data.py:198-199, DeepCoNN.py:53-54); conv windows inside such a trailing run all produce the same
+ * value and max_pool1d keeps the first, so a document whose rows s..T-1 are equal gives bit-identical
+ * (pooled, argmax) when cut to doc_len = min(T, s+3) rows, with arg-max positions >= doc_len mapped
+ * back by + (T - doc_len).  doc_order = documents by decreasing tile count (load balance).
+ * ws: r4r_doc_plan_ws_bytes() bytes of scratch. */
+int64_t r4r_doc_plan_ws_bytes(void);
+int r4r_doc_plan(const int64_t* idx, int64_t N, int T, int32_t* doc_len, int32_t* doc_order, void* ws,
+                 void* stream);
 
 /* Diagnostics: when `buf32_u64` (device, 32 x uint64) is non-NULL every later r4r_conv_pool_tc launch
  * writes the per-role cycle counters of its first CTA pair there (see conv_tc.cu); NULL turns it off. */
@@ -126,6 +139,32 @@ int r4r_adam_step(int nt, float* const* p_host, const float* const* g_host, floa
 /* *counter += 1 on the device: the step count of a CUDA-graph-captured optimizer (torch keeps
  * state['step'] as a device tensor for capturable=True; torch/optim/adam.py semantics). */
 int r4r_counter_inc(int32_t* counter, void* stream);
+
+/* ---- K8: row-sharded tables (new: the reference is single-process) -----------
+ * Row r of a table lives on rank r % P at local row r / P.  The lookups keep the semantics of the
+ * same nn.Embedding / Tensor.gather call sites as r4r_word_gather_f32 / r4r_rows_gather.
+ * Request message (int64 words): for every peer q a block of 1+cap words: [n_q, local_row_0 .. ].
+ * Row payloads are [q][cap][row_bytes]; request (q, j) comes back at slot q*cap + j. */
+/* flags[idx[i]] = 1 (int32 flags[V], zero before the first call of a step) */
+int r4r_shard_mark(const int64_t* idx, int64_t n, int64_t V, int32_t* flags, void* stream);
+/* compacts the flagged ids per owner in increasing id order into req[P][1+cap], writes
+ * slot[id] = owner*cap + position (or -1), and clears flags.  cap >= ceil(V/P). */
+int r4r_shard_plan(int32_t* flags, int64_t V, int P, int64_t cap, int64_t* req, int64_t* slot, void* stream);
+/* id tables: no de-duplication; pos[i] = slot of ids[i]; req is zeroed inside.  cap >= n. */
+int r4r_shard_bucket(const int64_t* ids, int64_t n, int64_t R, int P, int64_t cap, int64_t* req, int64_t* pos,
+                     void* stream);
+/* owner side: out[q][j][:] = shard[rreq(q, j)][:] for j < n_q.  row_bytes % 4 == 0. */
+int r4r_shard_serve(const void* shard, int64_t rows_local, int row_bytes, const int64_t* rreq, int P, int64_t cap,
+                    void* out, void* stream);
+/* fused gather + all-to-all: as r4r_shard_serve, but requester q's block is written to
+ * out_ptrs_host[q] -- rank q's receive buffer (+ this rank's block offset) mapped over NVLink. */
+int r4r_shard_serve_p2p(const void* shard, int64_t rows_local, int row_bytes, const int64_t* rreq, int P, int64_t cap,
+                        void* const* out_ptrs_host, void* stream);
+/* out[i] = slot[idx[i]]  (token ids -> rows of the per-step row cache) */
+int r4r_shard_remap(const int64_t* idx, int64_t n, const int64_t* slot, int64_t V, int64_t* out, void* stream);
+/* owner side of the backward: gtable[rreq(q, j)][:] += scale * grads[q*cap + j][:] for j < n_q */
+int r4r_shard_scatter_add(const float* grads, const int64_t* rreq, int P, int64_t cap, int L, float* gtable,
+                          int64_t rows_local, float scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -41,6 +41,7 @@
 // lines (measured 33.7 ms vs 3.7 ms per 4096 documents).
 #include "common.cuh"
 #include <stdlib.h>
+#include <type_traits>
 
 namespace {
 
@@ -55,8 +56,9 @@ constexpr int MMA_WARP = NUM_EPI_WARPS + NUM_PROD_WARPS;
 constexpr int NUM_THREADS = (MMA_WARP + 1) * 32;
 constexpr int MAX_SLOTS = 8;
 constexpr int ROWS_PER_THREAD = 9;     // producer thread i copies rows i/8 + 16k, k < 9
-constexpr int MAX_CPS = 32;            // 16-byte K-chunks per ring slot (<= 4 per producer thread and row)
-constexpr int LAG = 1;                 // a slab is published after the next one has been issued
+constexpr int CPS = 8;                 // 16-byte K-chunks per ring slab: one chunk column per producer lane (K = 64 per slab)
+constexpr int MAX_SPT = 16;            // slabs per position tile -> Kc <= 128 chunks (E <= 1024)
+constexpr int LAG = 2;                 // a slab is published after the next LAG ones have been issued
 
 struct SharedCtl {
   unsigned long long full[MAX_SLOTS];      // leader's copy is used: 2 CTAs x NUM_PROD_WARPS arrivals
@@ -126,8 +128,17 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // .ca keeps the gathered lines in L1 (see the header comment)
-__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(src_bytes) : "memory");
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+// 16-byte copy from [src + OFS] (compile-time byte offset folded into the instruction)
+template <int OFS>
+__device__ __forceinline__ void cp_async16_ca_ofs(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1+%2], 16;" :: "r"(dst), "l"(src), "n"(OFS) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
@@ -193,10 +204,20 @@ struct Params {
   int* argmax;
   int fmt;                   // 0 f16, 1 bf16
   int nslots;
-  int cps;                   // chunks per ring slot (even)
   int slot_bytes;
   unsigned long long* prof;  // diagnostics: per-role cycle counters of cluster 0 (r4r_conv_debug_profile), or NULL
+  const int* doc_len;        // [N] effective document lengths (r4r_doc_plan), or NULL = T for every document
+  const int* doc_order;      // [N] processing order (longest first), or NULL = identity
 };
+
+// Work item k of the launch -> (document, its effective length).  A document whose last rows repeat
+// one token (the reader's padding, data.py:198-199) is processed as if it ended three rows into that
+// run: all later windows would reproduce values already seen (see r4r_doc_plan in the header).
+__device__ __forceinline__ void work_item(const Params& P, long long k, long long& doc, int& Td) {
+  doc = P.doc_order ? (long long)__ldg(P.doc_order + k) : k;
+  Td = P.doc_len ? __ldg(P.doc_len + doc) : P.T;
+}
+__device__ __forceinline__ int tiles_of(int Td) { return (Td + 2 + 2 * TILE_M - 1) / (2 * TILE_M); }
 
 // ------------------------------------------------------------------------------------------
 // does (ov, op) beat (v, p)?  larger value, then smaller position
@@ -210,54 +231,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr) : "memory");
 }
 
-__host__ __device__ constexpr int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+__device__ __forceinline__ float redux_max_f32(float v) {
+  float m;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
+  return m;
+}
+__device__ __forceinline__ uint32_t redux_min_u32(uint32_t v) {
+  uint32_t m;
+  asm volatile("redux.sync.min.u32 %0, %1, 0xffffffff;" : "=r"(m) : "r"(v));
+  return m;
+}
 
-// Warp-wide (max value, smallest key) reduction of N columns held by every lane, as a transposing
-// butterfly: in the round with lane distance O each lane keeps one half of its columns and trades
-// the other half with its partner, so the column count halves per round and the whole reduction
-// costs ~N shuffle pairs instead of 5*N.  Column bit log2(N)-1-r ends up equal to lane bit 4-r.
-template <int N, int O>
-struct Butterfly {
-  static __device__ __forceinline__ void run(float (&v)[N], uint32_t (&key)[N], int lane) {
-    if constexpr (O > 0) {
-      const bool up = (lane & O) != 0;
-      if constexpr (N > 1) {
-        constexpr int H = N / 2;
-        float nv[H];
-        uint32_t nk[H];
-#pragma unroll
-        for (int c = 0; c < H; ++c) {
-          float mine = up ? v[c + H] : v[c];
-          uint32_t mk = up ? key[c + H] : key[c];
-          const float send = up ? v[c] : v[c + H];
-          const uint32_t sk = up ? key[c] : key[c + H];
-          const float rv = __shfl_xor_sync(0xffffffffu, send, O);
-          const uint32_t rk = __shfl_xor_sync(0xffffffffu, sk, O);
-          if (rv > mine || (rv == mine && rk < mk)) { mine = rv; mk = rk; }
-          nv[c] = mine;
-          nk[c] = mk;
-        }
-        Butterfly<H, O / 2>::run(nv, nk, lane);
-#pragma unroll
-        for (int c = 0; c < H; ++c) { v[c] = nv[c]; key[c] = nk[c]; }
-      } else {
-        const float rv = __shfl_xor_sync(0xffffffffu, v[0], O);
-        const uint32_t rk = __shfl_xor_sync(0xffffffffu, key[0], O);
-        if (rv > v[0] || (rv == v[0] && rk < key[0])) { v[0] = rv; key[0] = rk; }
-        Butterfly<1, O / 2>::run(v, key, lane);
-      }
-    }
-  }
-};
 
 template <int EC>   // accumulator columns handled by one epilogue warp = Npad / 2
 __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, uint32_t rank, int cluster_id, int nclusters,
                                               int warp, int lane) {
-  constexpr int P2 = next_pow2(EC);
-  constexpr int KEEP = P2 >= 32 ? P2 / 32 : 1;           // columns per lane after the butterfly
-  constexpr int SHIFT = P2 >= 32 ? 0 : (P2 == 16 ? 1 : 2); // lanes sharing one column: 1 << SHIFT
-  const int npos = P.T + 2;
-  const int npt = (npos + 2 * TILE_M - 1) / (2 * TILE_M);
   const int q = warp & 3, h = warp >> 2;
   const int row = q * 32 + lane;
   const uint32_t lane_base = (uint32_t)(q * 32) << 16;
@@ -265,15 +253,20 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
   uint32_t it = 0, ndoc = 0;
   const bool prof_on = P.prof != nullptr && cluster_id == 0;
   long long w_full = 0, w_bar = 0, w_xchg = 0, t_begin = clock64();
-  for (long long doc = cluster_id; doc < P.N; doc += nclusters, ++ndoc) {
+  for (long long k = cluster_id; k < P.N; k += nclusters, ++ndoc) {
+    long long doc;
+    int Td;
+    work_item(P, k, doc, Td);
+    const int npos = Td + 2;
+    const int npt = tiles_of(Td);
     // running maximum per filter column and the tile it came from (one byte per column, packed
     // four to a register)
-    float best[P2];
-    uint32_t btile[P2 / 4];
+    float best[EC];
+    uint32_t btile[EC / 4];
 #pragma unroll
-    for (int c = 0; c < P2; ++c) best[c] = -INFINITY;
+    for (int c = 0; c < EC; ++c) best[c] = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < P2 / 4; ++c) btile[c] = 0u;
+    for (int c = 0; c < EC / 4; ++c) btile[c] = 0u;
     for (int pt = 0; pt < npt; ++pt, ++it) {
       const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
       TIMED_WAIT(w_full, mbar_wait(&ctl->tmem_full[buf], ph));
@@ -313,22 +306,27 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
       if (lane == 0) mbar_arrive_cluster(leader_tmem_empty[buf]);
     }
     // ---- per-document reduction over the warp's 32 rows: max value, smallest position on ties.
-    // key = tile << 5 | lane orders positions within the warp (same CTA rank and lane quarter).
+    // Two warp-wide reductions per column (redux.sync -> CREDUX): the maximum, then the smallest
+    // key = tile << 5 | lane among the lanes that hold it (positions within one warp are ordered by
+    // tile, then lane: same CTA rank and lane quarter).  Lane c % 32 keeps column c.
     {
-      uint32_t key[P2];
+      float keep_v[(EC + 31) / 32];
+      uint32_t keep_k[(EC + 31) / 32];
 #pragma unroll
-      for (int c = 0; c < P2; ++c) key[c] = (((btile[c >> 2] >> (8 * (c & 3))) & 0xffu) << 5) | (uint32_t)lane;
-      Butterfly<P2, 16>::run(best, key, lane);
-      if ((lane & ((1 << SHIFT) - 1)) == 0) {
+      for (int c = 0; c < EC; ++c) {
+        const float m = redux_max_f32(best[c]);
+        const uint32_t tile = (btile[c >> 2] >> (8 * (c & 3))) & 0xffu;
+        const uint32_t kmin = redux_min_u32(best[c] == m ? ((tile << 5) | (uint32_t)lane) : 0xffffffffu);
+        if (lane == (c & 31)) { keep_v[c >> 5] = m; keep_k[c >> 5] = kmin; }
+      }
 #pragma unroll
-        for (int i = 0; i < KEEP; ++i) {
-          const int c = P2 >= 32 ? lane * KEEP + i : lane >> SHIFT;
-          if (c < EC) {
-            const float v = best[i];
-            ctl->red_val[warp][c] = v;
-            ctl->red_pos[warp][c] = v == -INFINITY ? 0x7fffffff
-                                                   : (int)(key[i] >> 5) * 2 * TILE_M + (int)rank * TILE_M + q * 32 + (int)(key[i] & 31u);
-          }
+      for (int i = 0; i < (EC + 31) / 32; ++i) {
+        const int c = lane + 32 * i;
+        if (c < EC) {
+          const float v = keep_v[i];
+          ctl->red_val[warp][c] = v;
+          ctl->red_pos[warp][c] = v == -INFINITY ? 0x7fffffff
+                                                 : (int)(keep_k[i] >> 5) * 2 * TILE_M + (int)rank * TILE_M + q * 32 + (int)(keep_k[i] & 31u);
         }
       }
     }
@@ -364,7 +362,8 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
         if (f < P.F) {
           const float o = v + __ldg(P.bias + f);
           P.pooled[doc * P.F + f] = o > 0.0f ? o : 0.0f;
-          P.argmax[doc * P.F + f] = p;
+          // positions Td, Td+1 of the shortened document are positions T, T+1 of the full one
+          P.argmax[doc * P.F + f] = (p >= Td && p < npos) ? p + (P.T - Td) : p;
         }
       }
     }
@@ -377,9 +376,7 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
 
 __device__ __forceinline__ void producer_role(const Params& P, SharedCtl* ctl, uint8_t* ring, uint32_t rank, int cluster_id,
                                               int nclusters, int ptid) {
-  const int npt = (P.T + 2 + 2 * TILE_M - 1) / (2 * TILE_M);
-  const int cps = P.cps;
-  const int spt = (P.Kc + cps - 1) / cps;                // slabs per tile
+  const int spt = (P.Kc + CPS - 1) / CPS;                // slabs per tile
   const int c8 = ptid & 7, r0 = ptid >> 3;
   const int lane = ptid & 31;
   const uint32_t ring_base = smem_u32(ring);
@@ -387,80 +384,90 @@ __device__ __forceinline__ void producer_role(const Params& P, SharedCtl* ctl, u
   const int nslots = P.nslots;
   const uint32_t leader_full0 = mapa(smem_u32(&ctl->full[0]), 0);
   const bool last_row = r0 + 16 * (ROWS_PER_THREAD - 1) < TILE_M + 2;   // rows 128, 129 exist for r0 < 2 only
+  // every producer lane copies ONE 16-byte chunk column (c8 + 8s in slab s) of its nine rows, so the
+  // global address of a copy is a per-row base + a compile-time offset (no address arithmetic per copy);
+  // conv padding rows read the all-zero row V of the shadow table (no src-size operand either)
+  const uint8_t* const thread_base = P.shadow + c8 * 16;
+  const uint8_t* const zero_row = thread_base + P.V * P.row_bytes;
+  const int last_slab_chunks = P.Kc - (spt - 1) * CPS;                  // chunk columns in the last slab
+  const bool in_last = c8 < last_slab_chunks;
 
   // Token ids of a tile's rows are fetched ONE TILE AHEAD into registers (unchecked, so the nine
   // loads are issued back to back and their HBM latency hides behind the current tile's slabs);
   // slot row r <-> document position pt*256 + rank*128 - 2 + r, -1 marks a zero (padding) row.
-  auto fetch = [&](long long doc, int pt, long long (&out)[ROWS_PER_THREAD]) {
+  auto fetch = [&](long long doc, int Td, int pt, long long (&out)[ROWS_PER_THREAD]) {
     const long long* drow = P.idx + doc * (long long)P.T;
 #pragma unroll
     for (int k = 0; k < ROWS_PER_THREAD; ++k) {
       const int r = r0 + 16 * k;
       const int pos = pt * 2 * TILE_M + (int)rank * TILE_M - 2 + r;
-      out[k] = (r < TILE_M + 2 && pos >= 0 && pos < P.T) ? __ldg(drow + pos) : -1LL;
+      out[k] = (r < TILE_M + 2 && pos >= 0 && pos < Td) ? __ldg(drow + pos) : -1LL;
     }
   };
-  // publish slab `n`: its copies have landed (wait_group), make them visible to the tensor cores
+  // publish a slab: its copies have landed (wait_group), make them visible to the tensor cores
   // (async proxy), then ONE arrival per warp on the leader CTA's barrier
-  auto publish = [&](uint32_t n) {
+  uint32_t sig_slot = 0;
+  auto publish = [&]() {
     fence_proxy_async();
     __syncwarp();
-    if (lane == 0) mbar_arrive_cluster(leader_full0 + (n % nslots) * 8u);
+    if (lane == 0) mbar_arrive_cluster(leader_full0 + sig_slot * 8u);
+    sig_slot = sig_slot + 1 == (uint32_t)nslots ? 0u : sig_slot + 1;
   };
 
   const bool prof_on = P.prof != nullptr && cluster_id == 0;
   long long w_empty = 0, w_group = 0, t_begin = clock64();
-  uint32_t issued = 0, signalled = 0;
-  long long doc = cluster_id;
-  int pt = 0;
+  uint32_t slot = 0, empty_parity = 1u;                  // parity the empty barrier shows once the slot is free
+  uint32_t pending = 0;                                  // slabs issued but not yet published
+  long long wk = cluster_id, doc = 0;
+  int pt = 0, Td = 0, npt = 0;
   long long cur[ROWS_PER_THREAD], nxt[ROWS_PER_THREAD];
-  if (doc < P.N) fetch(doc, 0, cur);
-  while (doc < P.N) {
-    long long ndoc = doc;
-    int pt_next = pt + 1;
-    if (pt_next == npt) { pt_next = 0; ndoc += nclusters; }
-    if (ndoc < P.N) fetch(ndoc, pt_next, nxt);
-    // per row: source pointer (any valid address for a zero row) and a mask of the zero rows
+  if (wk < P.N) {
+    work_item(P, wk, doc, Td);
+    npt = tiles_of(Td);
+    fetch(doc, Td, 0, cur);
+  }
+  while (wk < P.N) {
+    long long nk = wk, ndoc = doc;
+    int pt_next = pt + 1, nTd = Td, nnpt = npt;
+    if (pt_next == npt) {
+      pt_next = 0;
+      nk += nclusters;
+      if (nk < P.N) { work_item(P, nk, ndoc, nTd); nnpt = tiles_of(nTd); }
+    }
+    if (nk < P.N) fetch(ndoc, nTd, pt_next, nxt);
     const uint8_t* src[ROWS_PER_THREAD];
-    uint32_t zmask = 0u;
 #pragma unroll
     for (int k = 0; k < ROWS_PER_THREAD; ++k) {
       const long long tok = cur[k];
       if (tok < -1 || tok >= P.V) __trap();               // the reference device-asserts on OOB ids
-      src[k] = P.shadow + (tok < 0 ? 0 : tok) * P.row_bytes;
-      zmask |= tok < 0 ? (1u << k) : 0u;
+      src[k] = tok < 0 ? zero_row : thread_base + tok * P.row_bytes;
     }
-    for (int s = 0; s < spt; ++s, ++issued) {
-      const uint32_t slot = issued % nslots, round = issued / nslots;
-      TIMED_WAIT(w_empty, mbar_wait(&ctl->empty[slot], (round & 1u) ^ 1u));
-      const uint32_t dst = ring_base + slot * P.slot_bytes + dst_thread;
+    static_for<0, MAX_SPT>([&](auto sc) {
+      constexpr int s = decltype(sc)::value;
+      if (s < spt) {
+        TIMED_WAIT(w_empty, mbar_wait(&ctl->empty[slot], empty_parity));
+        const uint32_t dst = ring_base + slot * (uint32_t)P.slot_bytes + dst_thread;
+        if (s < spt - 1 || in_last) {
 #pragma unroll
-      for (int m = 0; m < MAX_CPS / 8; ++m) {
-        const int cl = c8 + 8 * m;                        // chunk within the slab
-        const int ch = s * cps + cl;                      // chunk within the window row
-        if (cl < cps && ch < P.Kc) {
-          const uint32_t d = dst + m * (8 * RA * 16);
-          const int off = ch * 16;
-#pragma unroll
-          for (int k = 0; k < ROWS_PER_THREAD - 1; ++k)
-            cp_async16_ca(d + k * 256, src[k] + off, (zmask >> k) & 1u ? 0u : 16u);
-          if (last_row) cp_async16_ca(d + (ROWS_PER_THREAD - 1) * 256, src[ROWS_PER_THREAD - 1] + off,
-                                      (zmask >> (ROWS_PER_THREAD - 1)) & 1u ? 0u : 16u);
+          for (int k = 0; k < ROWS_PER_THREAD - 1; ++k) cp_async16_ca_ofs<s * CPS * 16>(dst + k * 256, src[k]);
+          if (last_row) cp_async16_ca_ofs<s * CPS * 16>(dst + (ROWS_PER_THREAD - 1) * 256, src[ROWS_PER_THREAD - 1]);
         }
+        cp_async_commit();
+        ++pending;
+        if (pending > (uint32_t)LAG) {
+          TIMED_WAIT(w_group, cp_async_wait<LAG>(); publish());
+          --pending;
+        }
+        if (++slot == (uint32_t)nslots) { slot = 0; empty_parity ^= 1u; }
       }
-      cp_async_commit();
-      if (issued + 1 - signalled > (uint32_t)LAG) {
-        TIMED_WAIT(w_group, cp_async_wait<LAG>(); publish(signalled));
-        ++signalled;
-      }
-    }
+    });
 #pragma unroll
-    for (int k = 0; k < ROWS_PER_THREAD; ++k) cur[k] = nxt[k];
-    doc = ndoc;
+    for (int k2 = 0; k2 < ROWS_PER_THREAD; ++k2) cur[k2] = nxt[k2];
+    wk = nk; doc = ndoc; Td = nTd; npt = nnpt;
     pt = pt_next;
   }
   cp_async_wait<0>();
-  for (; signalled < issued; ++signalled) publish(signalled);
+  for (; pending > 0; --pending) publish();
   if (prof_on && ptid == 0) {
     unsigned long long* o = P.prof + rank * 16 + 4;
     o[0] = (unsigned long long)(clock64() - t_begin); o[1] = w_empty; o[2] = w_group;
@@ -469,9 +476,7 @@ __device__ __forceinline__ void producer_role(const Params& P, SharedCtl* ctl, u
 
 __device__ __forceinline__ void mma_role(const Params& P, SharedCtl* ctl, const uint8_t* bsm, const uint8_t* ring, int cluster_id,
                                          int nclusters, int lane) {
-  const int npt = (P.T + 2 + 2 * TILE_M - 1) / (2 * TILE_M);
-  const int cps = P.cps;
-  const int spt = (P.Kc + cps - 1) / cps;
+  const int spt = (P.Kc + CPS - 1) / CPS;
   const uint32_t idesc = umma_idesc(P.fmt, P.Npad);
   const uint32_t a_base = smem_u32(ring), b_base = smem_u32(bsm);
   const uint32_t a_lbo = RA * 16, b_lbo = (uint32_t)(P.Npad / 2) * 16;
@@ -484,24 +489,27 @@ __device__ __forceinline__ void mma_role(const Params& P, SharedCtl* ctl, const 
   const uint32_t a_lo0 = ((a_base >> 4) & 0x3FFFu) | (a_step << 16);
   const uint32_t b_lo0 = ((b_base >> 4) & 0x3FFFu) | (b_step << 16);
   const bool leader = elect_one();
-  uint32_t consumed = 0, it = 0;
+  uint32_t slot = 0, full_parity = 0u, it = 0;
   const bool prof_on = P.prof != nullptr && cluster_id == 0;
   long long w_tmem = 0, w_full = 0, t_begin = clock64();
-  for (long long doc = cluster_id; doc < P.N; doc += nclusters) {
+  for (long long k = cluster_id; k < P.N; k += nclusters) {
+    long long doc;
+    int Td;
+    work_item(P, k, doc, Td);
+    const int npt = tiles_of(Td);
     for (int pt = 0; pt < npt; ++pt, ++it) {
       const uint32_t buf = it & 1u, use = it >> 1;
       TIMED_WAIT(w_tmem, mbar_wait(&ctl->tmem_empty[buf], (use & 1u) ^ 1u));       // both CTAs' epilogues drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = ctl->tmem_base + buf * ACC_STRIDE;
-      for (int s = 0; s < spt; ++s, ++consumed) {
-        const uint32_t slot = consumed % nslots, round = consumed / nslots;
-        TIMED_WAIT(w_full, mbar_wait(&ctl->full[slot], round & 1u));               // both CTAs' producers published this slab
+      for (int s = 0; s < spt; ++s) {
+        TIMED_WAIT(w_full, mbar_wait(&ctl->full[slot], full_parity));              // both CTAs' producers published this slab
         tc_fence_after();
         if (leader) {
           // descriptors advance by constants: +2 K-chunks per K=16 step, +1 row (16 B) per window row j
-          const int nk = min(cps, P.Kc - s * cps) >> 1;        // K=16 steps in this slab
+          const int nk = min(CPS, P.Kc - s * CPS) >> 1;        // K=16 steps in this slab
           uint32_t a_lo = a_lo0 + ((slot * (uint32_t)P.slot_bytes) >> 4);
-          uint32_t b_lo = b_lo0 + (uint32_t)(s * cps) * b_step;
+          uint32_t b_lo = b_lo0 + (uint32_t)(s * CPS) * b_step;
           uint32_t acc = s ? 1u : 0u;
           for (int kk = 0; kk < nk; ++kk) {
             umma_f16_pair(d_tmem, mk_desc(a_lo, desc_hi), mk_desc(b_lo, desc_hi), idesc, acc);
@@ -515,6 +523,7 @@ __device__ __forceinline__ void mma_role(const Params& P, SharedCtl* ctl, const 
           if (s == spt - 1) umma_commit_pair(&ctl->tmem_full[buf]); // accumulator complete (both CTAs)
         }
         __syncwarp();
+        if (++slot == (uint32_t)nslots) { slot = 0; full_parity ^= 1u; }
       }
     }
   }
@@ -659,7 +668,8 @@ extern "C" int r4r_conv_pack_weights(const float* conv_w, int E, int F, void* wp
 extern "C" int r4r_conv_pool_tc(const void* shadow, int64_t V, int Epad, int E, int dtype,
                                 const int64_t* idx, int64_t N, int T,
                                 const void* wpack, const float* conv_b, int F,
-                                float* pooled, int32_t* argmax, void* stream) {
+                                float* pooled, int32_t* argmax,
+                                const int32_t* doc_len, const int32_t* doc_order, void* stream) {
   R4R_REQUIRE(shadow && idx && wpack && conv_b && pooled && argmax, R4R_EINVAL, "conv_pool_tc: null pointer");
   R4R_REQUIRE(V > 0 && E > 0 && T > 0 && N >= 0, R4R_EINVAL, "conv_pool_tc: bad sizes");
   R4R_REQUIRE((T + 2 + 2 * TILE_M - 1) / (2 * TILE_M) <= 256, R4R_EUNSUP, "conv_pool_tc: T=%d exceeds 256 position tiles", T);
@@ -667,6 +677,7 @@ extern "C" int r4r_conv_pool_tc(const void* shadow, int64_t V, int Epad, int E, 
   PackPlan pl;
   R4R_REQUIRE(make_plan(E, F, pl), R4R_EUNSUP, "conv_pool_tc: E=%d F=%d unsupported (F <= %d)", E, F, N_MAX);
   R4R_REQUIRE(Epad % 8 == 0 && Epad >= pl.Kc * 8, R4R_EINVAL, "conv_pool_tc: shadow row width Epad=%d must be a multiple of 8 and >= %d", Epad, pl.Kc * 8);
+  // NOTE: the shadow table must carry V+1 rows, row V all zero (r4r_shadow_build writes it): conv padding rows are read from it
   R4R_REQUIRE(reinterpret_cast<uintptr_t>(shadow) % 16 == 0 && reinterpret_cast<uintptr_t>(wpack) % 16 == 0, R4R_EINVAL, "conv_pool_tc: shadow/wpack must be 16-byte aligned");
   if (N == 0) return 0;
 
@@ -681,26 +692,16 @@ extern "C" int r4r_conv_pool_tc(const void* shadow, int64_t V, int Epad, int E, 
     R4R_REQUIRE(cc == 10, R4R_ENODEV, "conv_pool_tc: needs an sm_100 device (found cc %d.x)", cc);
     R4R_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
-  // shared-memory plan: [ctl][resident filter half][A ring of nslots x (cps chunks x RA rows x 16 B)]
+  // shared-memory plan: [ctl][resident filter half][A ring of nslots x (CPS chunks x RA rows x 16 B)]
   const long long ctl_bytes = (sizeof(SharedCtl) + 127) & ~127LL;
   const long long b_bytes = (pl.half_bytes + 127) & ~127LL;
   const long long avail = (long long)smem_optin - ctl_bytes - b_bytes - 1024;
-  int cps = 0, nslots = 0;
-  {
-    const char* e = getenv("R4R_CONV_CPS");                 // tuning override: chunks per ring slot
-    const int forced = e ? atoi(e) : 0;
-    for (int spt = 1; spt <= pl.Kc / 2 && !cps; ++spt) {
-      int c = (pl.Kc + spt - 1) / spt;
-      c += c & 1;
-      if (forced) c = forced + (forced & 1);
-      if (c > MAX_CPS) continue;
-      long long ns = avail / ((long long)c * RA * 16);
-      if (ns > MAX_SLOTS) ns = MAX_SLOTS;
-      if (ns >= LAG + 2 || forced) { cps = c; nslots = (int)ns; }
-    }
-  }
-  R4R_REQUIRE(cps >= 2 && nslots >= LAG + 2, R4R_EUNSUP, "conv_pool_tc: E=%d F=%d leaves no room for the A ring next to the filter bank", E, F);
-  const int slot_bytes = cps * RA * 16;
+  R4R_REQUIRE(pl.Kc <= CPS * MAX_SPT, R4R_EUNSUP, "conv_pool_tc: E=%d exceeds %d", E, CPS * MAX_SPT * 8);
+  long long ns = avail / ((long long)CPS * RA * 16);
+  if (ns > MAX_SLOTS) ns = MAX_SLOTS;
+  const int nslots = (int)ns;
+  R4R_REQUIRE(nslots >= LAG + 2, R4R_EUNSUP, "conv_pool_tc: E=%d F=%d leaves no room for the A ring next to the filter bank", E, F);
+  const int slot_bytes = CPS * RA * 16;
   const size_t smem_bytes = (size_t)(ctl_bytes + b_bytes + (long long)nslots * slot_bytes);
 
   Params P;
@@ -711,8 +712,10 @@ extern "C" int r4r_conv_pool_tc(const void* shadow, int64_t V, int Epad, int E, 
   P.N = N; P.T = T; P.Kc = pl.Kc; P.F = F; P.Npad = pl.Npad;
   P.wpack = static_cast<const uint8_t*>(wpack);
   P.bias = conv_b; P.pooled = pooled; P.argmax = argmax;
-  P.fmt = dtype; P.nslots = nslots; P.cps = cps; P.slot_bytes = slot_bytes;
+  P.fmt = dtype; P.nslots = nslots; P.slot_bytes = slot_bytes;
   P.prof = g_prof;
+  P.doc_len = doc_len;
+  P.doc_order = doc_order;
 
   R4R_CUDA(cudaFuncSetAttribute(conv_pool_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   long long nclusters = sm_count / 2;

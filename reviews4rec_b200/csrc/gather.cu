@@ -54,11 +54,11 @@ template <> __device__ __forceinline__ __nv_bfloat16 cvt_from_f32<__nv_bfloat16>
 template <typename T>
 __global__ void __launch_bounds__(256) shadow_build_kernel(const float* __restrict__ table, int64_t V, int E,
                                                            T* __restrict__ shadow, int Epad) {
-  const int64_t total = V * (int64_t)Epad;
+  const int64_t total = (V + 1) * (int64_t)Epad;        // row V = zeros (the conv's padding rows read it)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t v = i / Epad;
     int e = (int)(i - v * Epad);
-    shadow[i] = cvt_from_f32<T>(e < E ? table[v * (int64_t)E + e] : 0.0f);
+    shadow[i] = cvt_from_f32<T>((e < E && v < V) ? table[v * (int64_t)E + e] : 0.0f);
   }
 }
 
@@ -66,7 +66,7 @@ extern "C" int r4r_shadow_build(const float* table, int64_t V, int E, void* shad
   R4R_REQUIRE(table && shadow, R4R_EINVAL, "shadow_build: null pointer");
   R4R_REQUIRE(V > 0 && E > 0 && Epad >= E && Epad % 8 == 0, R4R_EINVAL, "shadow_build: need Epad>=E, Epad%%8==0 (E=%d Epad=%d)", E, Epad);
   R4R_REQUIRE(dtype == R4R_DT_F16 || dtype == R4R_DT_BF16, R4R_EINVAL, "shadow_build: dtype %d", dtype);
-  int64_t total = V * (int64_t)Epad;
+  int64_t total = (V + 1) * (int64_t)Epad;
   int64_t blocks = cdiv64(total, 256);
   if (blocks > 148 * 32) blocks = 148 * 32;
   if (dtype == R4R_DT_F16) shadow_build_kernel<__half><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(table, V, E, (__half*)shadow, Epad);

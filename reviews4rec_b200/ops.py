@@ -15,6 +15,13 @@ from ._lib import call
 NUM_FILTERS = 100          # common_pytorch_models.py:11
 _MODES = ("exact", "f16", "bf16")
 _conv_mode = os.environ.get("R4R_CONV_MODE", "f16")
+_doc_plan = os.environ.get("R4R_DOC_PLAN", "1") != "0"      # skip the repeated-padding tail of documents (exact)
+_PAIR_TILE = 256                                             # conv positions per CTA-pair tile of conv_pool_tc
+
+
+def set_doc_plan(on: bool) -> None:
+    global _doc_plan
+    _doc_plan = bool(on)
 
 
 def set_conv_mode(mode: str) -> None:
@@ -111,7 +118,7 @@ class ShadowTable:
             V, E = table.shape
             self.epad = ((E + 63) // 64) * 64                     # 128-byte aligned rows
             dt = torch.float16 if mode == "f16" else torch.bfloat16
-            self.tensor = torch.empty(V, self.epad, device=table.device, dtype=dt)
+            self.tensor = torch.empty(V + 1, self.epad, device=table.device, dtype=dt)   # row V: zeros (conv padding)
             call("r4r_shadow_build", _p(table), V, E, _p(self.tensor), self.epad,
                  _lib.R4R_DT_F16 if mode == "f16" else _lib.R4R_DT_BF16, _stream())
             self._key = key
@@ -145,9 +152,17 @@ def conv_pool_forward(idx: torch.Tensor, table: torch.Tensor, conv_w: torch.Tens
             raise RuntimeError("conv_pool_tc: unsupported shape E=%d F=%d" % (E, F))
         wpack = torch.empty(nbytes, device=table.device, dtype=torch.uint8)
         call("r4r_conv_pack_weights", _p(conv_w), E, F, _p(wpack), dt, _stream())
+        doc_len = doc_order = None
+        if _doc_plan and T + 2 > _PAIR_TILE and N > 0:
+            # documents padded with a repeated token are cut to their informative prefix (exact, see
+            # r4r_doc_plan in include/r4r_b200.h) and issued longest first
+            doc_len = torch.empty(N, device=table.device, dtype=torch.int32)
+            doc_order = torch.empty(N, device=table.device, dtype=torch.int32)
+            ws = torch.empty(_lib.lib.r4r_doc_plan_ws_bytes(), device=table.device, dtype=torch.uint8)
+            call("r4r_doc_plan", _p(idx), N, T, _p(doc_len), _p(doc_order), _p(ws), _stream())
         with _ConvTimer():
             call("r4r_conv_pool_tc", _p(sh), V, shadow.epad, E, dt, _p(idx), N, T, _p(wpack), _p(conv_b), F,
-                 _p(pooled), _p(argmax), _stream())
+                 _p(pooled), _p(argmax), _p(doc_len), _p(doc_order), _stream())
     return pooled, argmax
 
 

@@ -34,16 +34,20 @@ sh = ops.ShadowTable()
 for i in range(2):
     ops.conv_pool_forward(pool[0], table, w, b, a.mode, sh)
 torch.cuda.synchronize()
-ts = []
+ts, tot = [], []
 for i in range(a.iters):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sink = []
     ops.set_conv_event_sink(sink)
+    e0.record()
     ops.conv_pool_forward(pool[i % 3], table, w, b, a.mode, sh)
+    e1.record()
     ops.set_conv_event_sink(None)
     torch.cuda.synchronize()
     ts.append(sink[0][0].elapsed_time(sink[0][1]))
+    tot.append(e0.elapsed_time(e1))
 ms = sum(ts) / len(ts)
+print("whole call (pack + plan + conv): %.3f ms" % (sum(tot) / len(tot)))
 fl = 2.0 * (a.T + 2) * 100 * 3 * a.E * a.docs
 print("conv_bench dist=%s docs=%d mode=%s env=%s: %.3f ms/launch  %.1f TFLOP/s  %.0f docs/s  alg %.0f GB/s" % (
     a.dist, a.docs, a.mode, {k: v for k, v in os.environ.items() if k.startswith("R4R_")}, ms, fl / ms / 1e9,

@@ -52,9 +52,9 @@ def test_shadow_table(R, mode, dt):
     table = torch.randn(123, 300, generator=gen(2)).cuda()
     sh = ops.ShadowTable()
     t = sh.get(table, mode)
-    assert t.shape == (123, 320) and t.dtype == dt
-    assert torch.equal(t[:, :300].cpu(), table.cpu().to(dt))   # round-to-nearest-even, bit-exact
-    assert float(t[:, 300:].abs().max()) == 0.0
+    assert t.shape == (124, 320) and t.dtype == dt              # V rows + the all-zero row the conv padding reads
+    assert torch.equal(t[:123, :300].cpu(), table.cpu().to(dt))   # round-to-nearest-even, bit-exact
+    assert float(t[:, 300:].abs().max()) == 0.0 and float(t[123].abs().max()) == 0.0
     assert sh.get(table, mode) is t                              # cached while the table is unchanged
     table.add_(1.0)
     assert sh.get(table, mode) is not t                          # version bump -> rebuilt
@@ -138,6 +138,79 @@ def test_conv_pool_tensor_core(R, O, mode, dt, N, T, E, V, Fn):
     ex_pooled, _ = O.conv_pool(O.word_gather(table, idx), w, b)
     tol = 2e-2 if mode == "bf16" else 3e-3
     assert_close(pooled, ex_pooled, rtol=tol, atol=tol, msg="pooled vs fp32 oracle")
+
+
+def _ragged_docs(seed, N, T, V):
+    """Documents whose tails repeat one token (id 0 or any other id) for run lengths that straddle
+    every boundary the work plan cares about: 0..5 rows, whole document, tile edges."""
+    g = gen(seed)
+    idx = torch.randint(1, V, (N, T), generator=g, dtype=torch.int64)
+    runs = [0, 1, 2, 3, 4, 5, T, T - 1, T - 2, T // 2] + [T - s for s in (253, 254, 255, 256, 257, 258, 509, 510, 511, 512, 513) if s < T]
+    for n in range(N):
+        r = runs[n] if n < len(runs) else int(torch.randint(0, T + 1, (1,), generator=g))
+        tok = 0 if n % 3 else int(torch.randint(1, V, (1,), generator=g))
+        if r > 0:
+            idx[n, T - r:] = tok
+    return idx
+
+
+@pytest.mark.parametrize("N,T", [(40, 1000), (25, 600), (12, 257), (9, 300)])
+def test_doc_plan_kernel(R, N, T):
+    """r4r_doc_plan: doc_len = min(T, start of the trailing run + 3); doc_order = permutation by
+    decreasing CTA-pair tile count."""
+    import ctypes
+    from reviews4rec_b200 import _lib
+    idx = _ragged_docs(5, N, T, 50)
+    d = idx.cuda()
+    doc_len = torch.empty(N, dtype=torch.int32, device="cuda")
+    order = torch.empty(N, dtype=torch.int32, device="cuda")
+    ws = torch.empty(_lib.lib.r4r_doc_plan_ws_bytes(), dtype=torch.uint8, device="cuda")
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    _lib.call("r4r_doc_plan", vp(d), N, T, vp(doc_len), vp(order), vp(ws), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    want = []
+    for n in range(N):
+        row = idx[n].tolist()
+        s = T - 1
+        while s > 0 and row[s - 1] == row[T - 1]:
+            s -= 1
+        want.append(min(T, s + 3))
+    assert doc_len.cpu().tolist() == want
+    o = order.cpu().tolist()
+    assert sorted(o) == list(range(N))
+    tiles = [(want[n] + 2 + 255) // 256 for n in o]
+    assert tiles == sorted(tiles, reverse=True)
+
+
+@pytest.mark.parametrize("mode", ["f16", "bf16"])
+@pytest.mark.parametrize("N,T,E,V", [(160, 1000, 300, 500), (40, 600, 64, 90), (33, 257, 32, 50)])
+def test_conv_doc_plan_is_exact(R, O, mode, N, T, E, V):
+    """Cutting documents to their informative prefix must not change a single bit of (pooled, argmax),
+    and the arg-max must be the FIRST maximum like F.max_pool1d's."""
+    from reviews4rec_b200 import ops
+    g = gen(77)
+    table = (torch.randn(V, E, generator=g) * 0.5).cuda()
+    w = (torch.randn(100, 1, 3, E, generator=g) * (1.0 / (3 * E) ** 0.5)).cuda()
+    b = (torch.randn(100, generator=g) * 0.1).cuda()
+    idx = _ragged_docs(6, N, T, V).cuda()
+    try:
+        ops.set_doc_plan(False)
+        p0, a0 = ops.conv_pool_forward(idx, table, w, b, mode)
+        ops.set_doc_plan(True)
+        p1, a1 = ops.conv_pool_forward(idx, table, w, b, mode)
+    finally:
+        ops.set_doc_plan(True)
+    torch.cuda.synchronize()
+    assert torch.equal(p0, p1), "pooled changed: max diff %.3e" % float((p0 - p1).abs().max())
+    assert torch.equal(a0, a1), "argmax changed at %d entries" % int((a0 != a1).sum())
+    dt = torch.float16 if mode == "f16" else torch.bfloat16
+    t_r, w_r = table.cpu().to(dt).float(), w.cpu().to(dt).float()
+    ref_pooled, ref_arg = O.conv_pool(O.word_gather(t_r, idx.cpu()), w_r, b.cpu())
+    assert_close(p1, ref_pooled, rtol=2e-4, atol=2e-4, msg="pooled vs oracle on rounded operands")
+    _check_argmax(O, t_r, idx.cpu(), w_r, b.cpu(), p1.cpu().double(), a1.cpu(), 2e-4)
+    # where the maximum lies inside the repeated tail the first-max position must match the oracle's
+    live = ref_pooled > 0
+    agree = (a1.cpu().long() == ref_arg)[live].float().mean()
+    assert float(agree) > 0.99, "argmax agreement with F.max_pool1d only %.4f" % float(agree)
 
 
 @pytest.mark.parametrize("N,T,E,V,Fn", [(6, 20, 12, 40, 100), (9, 333, 300, 900, 100), (40, 50, 7, 30, 100), (17, 64, 64, 100, 37)])
