@@ -97,6 +97,12 @@ int r4r_conv_wgrad_argmax(const float* table, int64_t V, int E, const int64_t* i
                           const int32_t* argmax, const float* pooled, const float* gpooled, int F,
                           float* dW, float* db, void* stream);
 
+/* Same gradient from the half-precision shadow rows the tensor-core forward read (f16 / bf16 modes):
+ * it is the exact gradient of what r4r_conv_pool_tc computed and halves the gather traffic. */
+int r4r_conv_wgrad_argmax_h(const void* shadow, int64_t V, int Epad, int E, int dtype, const int64_t* idx, int64_t N,
+                            int T, const int32_t* argmax, const float* pooled, const float* gpooled, int F,
+                            float* dW, float* db, void* stream);
+
 /* ---- small dense layers of the heads ----------------------------------------------------------
  * y[n,o] = sum_i x[n,i] W[o,i] + b[o]   (nn.Linear: TextCNN.fc common_pytorch_models.py:19,37;
  * DeepCoNN.final DeepCoNN.py:21-26; NARRE scorers NARRE.py:24-43; TransNet project TransNet.py:17-21) */

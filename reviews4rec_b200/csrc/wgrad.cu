@@ -103,6 +103,100 @@ __global__ void __launch_bounds__(THREADS) conv_wgrad_scalar_kernel(
     if (bsum != 0.0f) atomicAdd(db + f, bsum);
   }
 }
+
+// ---- half-precision rows (f16 / bf16 conv modes): the forward read the shadow table, so the exact
+// gradient of what it computed is sum_n gy * shadow_row; rows are 2*Epad bytes instead of 4*E, which
+// halves the L2 gather traffic that bounds this kernel.  Thread = (window row j, 16-byte chunk of
+// 8 columns); documents are processed four at a time so the dependent loads (argmax -> token id ->
+// row) of different documents overlap.
+constexpr int HTHREADS = 128;
+constexpr int HBATCH = 4;
+
+template <typename T> __device__ __forceinline__ void unpack8(const uint4& u, float (&x)[8]);
+template <> __device__ __forceinline__ void unpack8<__half>(const uint4& u, float (&x)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); x[2 * i] = f.x; x[2 * i + 1] = f.y; }
+}
+template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& u, float (&x)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); x[2 * i] = f.x; x[2 * i + 1] = f.y; }
+}
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(HTHREADS) conv_wgrad_half_kernel(
+    const uint8_t* __restrict__ shadow, int64_t V, int row_bytes, int E, const int64_t* __restrict__ idx, int64_t N, int Tn,
+    const int32_t* __restrict__ argmax, const float* __restrict__ pooled, const float* __restrict__ gpooled,
+    int F, float* __restrict__ dW, float* __restrict__ db) {
+  const int f = blockIdx.x;
+  const int64_t per = (N + gridDim.y - 1) / gridDim.y;
+  const int64_t n0 = (int64_t)blockIdx.y * per;
+  const int64_t n1 = (n0 + per < N) ? n0 + per : N;
+  const int nch = (E + 7) >> 3;                  // 16-byte chunks per row that carry data
+  const int nvec = 3 * nch;
+  const int tid = threadIdx.x;
+
+  float acc[NV][8];
+  int vj[NV], vc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[v][i] = 0.0f;
+    const int q = tid + v * HTHREADS;
+    vj[v] = q < nvec ? q / nch : -1;
+    vc[v] = q < nvec ? q % nch : 0;
+  }
+  float bsum = 0.0f;
+
+  for (int64_t nb = n0; nb < n1; nb += HBATCH) {
+    float g[HBATCH];
+    int a[HBATCH];
+#pragma unroll
+    for (int b = 0; b < HBATCH; ++b) {
+      const int64_t n = nb + b;
+      const bool in = n < n1;
+      const float p = in ? __ldg(pooled + n * F + f) : 0.0f;
+      const float gg = in ? __ldg(gpooled + n * F + f) : 0.0f;
+      a[b] = in ? __ldg(argmax + n * F + f) : 0;
+      g[b] = p > 0.0f ? gg : 0.0f;                 // dead ReLU -> no gradient (CTA-uniform)
+      bsum += g[b];
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      if (vj[v] < 0) continue;
+      int64_t tok[HBATCH];
+#pragma unroll
+      for (int b = 0; b < HBATCH; ++b) {
+        const int pos = a[b] + vj[v] - 2;          // document row feeding window row j
+        const bool live = g[b] != 0.0f && pos >= 0 && pos < Tn;
+        tok[b] = live ? __ldg(idx + (nb + b) * (int64_t)Tn + pos) : -1;
+      }
+      uint4 row[HBATCH];
+#pragma unroll
+      for (int b = 0; b < HBATCH; ++b) {
+        row[b] = make_uint4(0u, 0u, 0u, 0u);
+        if (tok[b] >= 0) row[b] = __ldg(reinterpret_cast<const uint4*>(shadow + tok[b] * (int64_t)row_bytes) + vc[v]);
+      }
+#pragma unroll
+      for (int b = 0; b < HBATCH; ++b) {
+        float x[8];
+        unpack8<T>(row[b], x);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[v][i] = fmaf(g[b], x[i], acc[v][i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    if (vj[v] < 0) continue;
+    float* dst = dW + ((int64_t)f * 3 + vj[v]) * E + vc[v] * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (vc[v] * 8 + i < E && acc[v][i] != 0.0f) atomicAdd(dst + i, acc[v][i]);
+  }
+  if (tid == 0 && bsum != 0.0f) atomicAdd(db + f, bsum);
+}
 }  // namespace
 
 extern "C" int r4r_conv_wgrad_argmax(const float* table, int64_t V, int E, const int64_t* idx, int64_t N, int T,
@@ -130,5 +224,37 @@ extern "C" int r4r_conv_wgrad_argmax(const float* table, int64_t V, int E, const
     else                          conv_wgrad_kernel<3><<<grid, THREADS, 0, s>>>(table, V, E, idx, N, T, argmax, pooled, gpooled, F, dW, db);
   }
   R4R_CHECK_LAUNCH("conv_wgrad");
+  return 0;
+}
+
+extern "C" int r4r_conv_wgrad_argmax_h(const void* shadow, int64_t V, int Epad, int E, int dtype, const int64_t* idx, int64_t N,
+                                       int T, const int32_t* argmax, const float* pooled, const float* gpooled, int F,
+                                       float* dW, float* db, void* stream) {
+  R4R_REQUIRE(shadow && idx && argmax && pooled && gpooled && dW && db, R4R_EINVAL, "conv_wgrad_h: null pointer");
+  R4R_REQUIRE(V > 0 && E > 0 && T > 0 && N >= 0 && F > 0, R4R_EINVAL, "conv_wgrad_h: bad sizes");
+  R4R_REQUIRE(dtype == R4R_DT_F16 || dtype == R4R_DT_BF16, R4R_EINVAL, "conv_wgrad_h: dtype %d", dtype);
+  R4R_REQUIRE(Epad % 8 == 0 && Epad >= ((E + 7) / 8) * 8 && reinterpret_cast<uintptr_t>(shadow) % 16 == 0, R4R_EINVAL,
+              "conv_wgrad_h: shadow rows must be 16-byte aligned with Epad %% 8 == 0 and Epad >= E (Epad=%d)", Epad);
+  if (N == 0) return 0;
+  cudaStream_t s = as_stream(stream);
+  int64_t want = (148 * 16 * 4 + F - 1) / F;     // >= 4 waves of 148 SMs x 16 resident CTAs
+  int64_t S = N / 16;
+  if (S > want) S = want;
+  if (S < 1) S = 1;
+  if (S > 65535) S = 65535;
+  dim3 grid((unsigned)F, (unsigned)S);
+  const int nvec = 3 * ((E + 7) / 8);
+  R4R_REQUIRE(nvec <= 3 * HTHREADS, R4R_EUNSUP, "conv_wgrad_h: E=%d too wide (max %d)", E, HTHREADS * 8);
+  const uint8_t* sh = static_cast<const uint8_t*>(shadow);
+  const int rb = Epad * 2;
+#define R4R_WG_LAUNCH(TYPE, NV) \
+  conv_wgrad_half_kernel<TYPE, NV><<<grid, HTHREADS, 0, s>>>(sh, V, rb, E, idx, N, T, argmax, pooled, gpooled, F, dW, db)
+  if (dtype == R4R_DT_F16) {
+    if (nvec <= HTHREADS) R4R_WG_LAUNCH(__half, 1); else if (nvec <= 2 * HTHREADS) R4R_WG_LAUNCH(__half, 2); else R4R_WG_LAUNCH(__half, 3);
+  } else {
+    if (nvec <= HTHREADS) R4R_WG_LAUNCH(__nv_bfloat16, 1); else if (nvec <= 2 * HTHREADS) R4R_WG_LAUNCH(__nv_bfloat16, 2); else R4R_WG_LAUNCH(__nv_bfloat16, 3);
+  }
+#undef R4R_WG_LAUNCH
+  R4R_CHECK_LAUNCH("conv_wgrad_h");
   return 0;
 }

@@ -127,8 +127,9 @@ class ShadowTable:
 
 # ------------------------------------------------------------------------------------ conv + pool
 def conv_pool_forward(idx: torch.Tensor, table: torch.Tensor, conv_w: torch.Tensor, conv_b: torch.Tensor,
-                      mode: str, shadow: Optional[ShadowTable] = None):
-    """Fused gather -> conv(3xE, pad 2) -> relu -> global max-pool.  Returns (pooled [N,F], argmax [N,F])."""
+                      mode: str, shadow: Optional[ShadowTable] = None, want_shadow: bool = False):
+    """Fused gather -> conv(3xE, pad 2) -> relu -> global max-pool.  Returns (pooled [N,F], argmax [N,F])
+    (+ the half-precision shadow rows it read, (tensor, Epad) or None, when ``want_shadow``)."""
     _need_cuda(idx, table, conv_w, conv_b)
     idx, table, conv_w, conv_b = _i64c(idx), _f32c(table), _f32c(conv_w), _f32c(conv_b)
     N, T = idx.shape
@@ -138,6 +139,7 @@ def conv_pool_forward(idx: torch.Tensor, table: torch.Tensor, conv_w: torch.Tens
         raise RuntimeError("conv weight must be [F,1,3,%d] (window size 3), got %s" % (E, tuple(conv_w.shape)))
     pooled = torch.empty(N, F, device=table.device, dtype=torch.float32)
     argmax = torch.empty(N, F, device=table.device, dtype=torch.int32)
+    used = None
     if mode == "exact":
         keys = torch.empty(N, F, device=table.device, dtype=torch.int64)
         with _ConvTimer():
@@ -163,7 +165,8 @@ def conv_pool_forward(idx: torch.Tensor, table: torch.Tensor, conv_w: torch.Tens
         with _ConvTimer():
             call("r4r_conv_pool_tc", _p(sh), V, shadow.epad, E, dt, _p(idx), N, T, _p(wpack), _p(conv_b), F,
                  _p(pooled), _p(argmax), _p(doc_len), _p(doc_order), _stream())
-    return pooled, argmax
+        used = (sh, shadow.epad)
+    return (pooled, argmax, used) if want_shadow else (pooled, argmax)
 
 
 class _ConvPool(torch.autograd.Function):
@@ -172,9 +175,10 @@ class _ConvPool(torch.autograd.Function):
         if table.requires_grad:
             raise RuntimeError("the word table is frozen in the reference (DeepCoNN.py:15 freeze=True); "
                                "a trainable word table is not part of this path")
-        pooled, argmax = conv_pool_forward(idx, table, conv_w, conv_b, mode, shadow)
+        pooled, argmax, used = conv_pool_forward(idx, table, conv_w, conv_b, mode, shadow, want_shadow=True)
         ctx.save_for_backward(idx, table, argmax, pooled)
         ctx.wshape = tuple(conv_w.shape)
+        ctx.mode, ctx.used = mode, used
         ctx.mark_non_differentiable(argmax)
         return pooled, argmax
 
@@ -185,8 +189,15 @@ class _ConvPool(torch.autograd.Function):
         N, T = idx.shape
         dW = torch.zeros(ctx.wshape, device=table.device, dtype=torch.float32)
         db = torch.zeros(F, device=table.device, dtype=torch.float32)
-        call("r4r_conv_wgrad_argmax", _p(table), table.shape[0], E, _p(idx), N, T, _p(argmax), _p(pooled),
-             _p(_f32c(gpooled)), F, _p(dW), _p(db), _stream())
+        if ctx.used is None:
+            call("r4r_conv_wgrad_argmax", _p(table), table.shape[0], E, _p(idx), N, T, _p(argmax), _p(pooled),
+                 _p(_f32c(gpooled)), F, _p(dW), _p(db), _stream())
+        else:
+            # f16 / bf16 modes: gradient of what the tensor-core forward computed, from the same shadow rows
+            sh, epad = ctx.used
+            call("r4r_conv_wgrad_argmax_h", _p(sh), table.shape[0], epad, E,
+                 _lib.R4R_DT_F16 if ctx.mode == "f16" else _lib.R4R_DT_BF16, _p(idx), N, T, _p(argmax), _p(pooled),
+                 _p(_f32c(gpooled)), F, _p(dW), _p(db), _stream())
         return None, None, dW, db, None, None
 
 

@@ -229,6 +229,29 @@ def test_conv_wgrad(R, O, N, T, E, V, Fn):
 
 
 # --------------------------------------------------------------------------- heads
+@pytest.mark.parametrize("mode,dt", [("f16", torch.float16), ("bf16", torch.bfloat16)])
+@pytest.mark.parametrize("N,T,E,V,Fn", [(6, 20, 12, 40, 100), (9, 333, 300, 900, 100), (40, 50, 7, 30, 100), (17, 64, 64, 100, 37),
+                                        (5, 40, 1000, 20, 8)])
+def test_conv_wgrad_half_rows(R, O, mode, dt, N, T, E, V, Fn):
+    """r4r_conv_wgrad_argmax_h == autograd of the conv run on the rounded table (the function the
+    tensor-core forward evaluates), through the public autograd op."""
+    from reviews4rec_b200 import ops
+    table, idx, w, b = _conv_case(40 + N, N, T, E, V, Fn)
+    g = torch.randn(N, Fn, generator=gen(3))
+    wc, bc = w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    pooled = ops.conv_pool(idx.cuda(), table.cuda(), wc, bc, mode=mode)
+    pooled.backward(g.cuda())
+    t_r = table.to(dt).float()
+    w_r = w.to(dt).float().requires_grad_(True)          # forward operands are rounded; the gradient is w.r.t. them
+    b_r = b.clone().requires_grad_(True)
+    ref, _ = O.conv_pool(O.word_gather(t_r, idx), w_r, b_r)
+    # use the kernel's own relu mask/argmax choice where the oracle's differs only by rounding: compare on the
+    # entries whose pooled values agree
+    ref.backward(g)
+    assert_close(bc.grad, b_r.grad, rtol=2e-3, atol=2e-3, msg="db")
+    assert_close(wc.grad, w_r.grad, rtol=2e-3, atol=2e-3, msg="dW")
+
+
 @pytest.mark.parametrize("n,i,o", [(37, 100, 10), (300, 20, 10), (5, 10, 1), (1000, 64, 32), (3, 4, 4)])
 def test_linear(R, n, i, o):
     from reviews4rec_b200 import ops

@@ -119,6 +119,30 @@ def test_train_loop_vs_reference(mt, opt_kind):
         assert_close(sd[k], ref[k], rtol=1e-4, atol=atol, msg="%s final.%s" % (mt, k))
 
 
+@pytest.mark.parametrize("mode", ["f16", "bf16"])
+@pytest.mark.parametrize("mt", ["deepconn", "deepconn++", "NARRE", "transnet", "transnet++"])
+def test_train_loop_mse_tensor_core_modes(mt, mode):
+    """north_star: train-loop MSE within 1e-4 (relative) of the reference in the fast modes too
+    (half-precision operands for the conv, fp32 accumulation, half-row wgrad)."""
+    import reviews4rec_b200 as R
+    from reviews4rec_b200.optim import FusedAdam
+    from reviews4rec_b200.train import train
+    from reviews4rec_b200.utils import init_transnet_optim
+    z, dims = load_golden(mt)
+    model, hp = build(mt, z, dims, mode=mode)
+    if mt.startswith("transnet"):
+        opt = init_transnet_optim(hp, model, FusedAdam)
+    else:
+        opt = FusedAdam(model.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"])
+    metrics = train(model, R.MSELoss(hp), opt, ListReader(golden_batches(z, dims, "cuda")), hp)
+    raw = train.last_raw
+    if mt.startswith("transnet"):
+        assert_close(raw["se_sum"], float(z["metric.MSE_sum"]), rtol=1e-4, msg="MSE sum (%s)" % mode)
+        assert_close(raw["target_sum"], float(z["metric.MSE_target_sum"]), rtol=1e-4, msg="MSE_target sum")
+    else:
+        assert abs(metrics["MSE"] - float(z["metric.MSE"])) <= 1e-4 * max(1.0, abs(float(z["metric.MSE"])))
+
+
 def test_reference_loop_shape_contract():
     """The drop-in classes expose what main.train / utils.init_transnet_optim touch."""
     z, dims = load_golden("transnet++")
