@@ -36,6 +36,8 @@ HP = {"model_type": "deepconn", "latent_size": 10, "word_embed_size": 300, "inpu
       "total_users": 1000000, "total_items": 100000, "lr": 0.002, "weight_decay": 1e-6, "batch_size": 4096,
       "narre_num_reviews": 10, "narre_num_words": 200}
 METRIC = "train ratings/sec DeepCoNN synthetic Amazon-shape"
+# dram__bytes_read.sum + dram__bytes_write.sum of one conv_pool_tc launch at B=4096 (ncu --set full, profiles/)
+NCU_CONV_DRAM_BYTES_PER_LAUNCH = 67.2e6
 REF_SAMPLE_B = 128            # ratings per reference-arm step (the reference's own default batch, hyper_params.py:60)
 
 
@@ -187,6 +189,8 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     group = None
     if world > 1:
+        import faulthandler
+        faulthandler.dump_traceback_later(max(300, args.steps), exit=True)   # a hung collective must not run forever
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
@@ -196,6 +200,20 @@ def run_b200(args):
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
     ops.set_conv_mode(args.conv_mode)
     model = build_model(hp, dev, seed=1)                   # same seed on every rank: replicas start identical
+    parallelism = "single GPU"
+    if world > 1 or args.force_shard:
+        # north_star: word + id tables row-sharded (row r on rank r % P), all-to-all index lookups;
+        # ratings split across ranks (weak scaling), dense-gradient all-reduce inside the captured step
+        from reviews4rec_b200 import sharded
+        tr = sharded.Transport(group)
+        wtr = None
+        if args.table == "sharded" and args.transport == "p2p" and world > 1:
+            wtr = sharded.P2PTransport.for_word_table(V_WORDS, hp["word_embed_size"], group)
+        sharded.shard_model(model, tr, shard_word_table=(args.table == "sharded"), word_transport=wtr)
+        parallelism = "dp%d, ratings split across ranks; %s; id/bias tables row-sharded; dense-grad all-reduce" % (
+            world, ("word table row-sharded r%%P, per-step de-duplicated lookup over %s" % (
+                "NVLink peer stores (fused gather + all-to-all kernel)" if wtr else "NCCL all-to-all")) if args.table == "sharded"
+            else "frozen word table replicated")
     model.train()
     criterion = MSELoss(hp)
     opt = FusedAdam(model.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"], capturable=True)
@@ -205,6 +223,13 @@ def run_b200(args):
     pool_n = max(2, min(8, -(-160 * 2 ** 20 // per_batch)))
     res = SyntheticReader(hp, B, pool_n, V_WORDS, seed=1234, device=dev, rank=rank)
     host = SyntheticReader(hp, B, pool_n, V_WORDS, seed=4321, device=None, pin=True, rank=rank)
+
+    # conv positions the launches actually process (documents cut to their informative prefix, exact)
+    pos_sum = 0
+    for d, _ in res.batches:
+        for idx in (d[3], d[4]):
+            pos_sum += int(ops.doc_lengths(idx).sum().item()) + 2 * idx.shape[0]
+    positions_per_launch = pos_sum / (2.0 * len(res.batches)) if ops.get_doc_plan() else float(B * (hp["input_length"] + 2))
 
     se_sum = torch.zeros(1, device=dev, dtype=torch.float32)
     conv_events = []
@@ -303,6 +328,8 @@ def run_b200(args):
 
     # ---- dominant kernel timed stand-alone if the in-graph events were unavailable
     timing = "cuda events bracketing the kernel inside the captured step, last %d steps of the timed region" % used
+    if not conv_ms and world > 1:
+        conv_ms = [float("nan")]
     if not conv_ms:
         d, y = res.batches[0]
         conv = model.user_conv.convs[0]
@@ -320,16 +347,19 @@ def run_b200(args):
         timing = "cuda events around stand-alone launches on the bench batches (in-graph events unavailable)"
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
 
     hbm_peak, tf_peak, peak_kind = measured_peaks()
     conv_avg_ms = sum(conv_ms) / len(conv_ms)
-    bytes_per_launch = B * hp["input_length"] * (8 + 4 * hp["word_embed_size"])          # one tower = one doc per rating
-    achieved = bytes_per_launch / (conv_avg_ms * 1e-3) / 1e9
-    tflops = B * conv_flops_per_doc(hp) / (conv_avg_ms * 1e-3) / 1e12
     step_ms = ms_total / K
+    E, T = hp["word_embed_size"], hp["input_length"]
+    # FLOPs one launch executes: sum over its documents of (informative rows + 2 conv positions) x F x 3E x 2
+    # (the padding-run shortcut is exact); algorithmic = the reference's dense conv over all T+2 positions
+    exec_flops = positions_per_launch * 100 * 3 * E * 2.0
+    alg_flops = B * conv_flops_per_doc(hp)
+    tflops = exec_flops / (conv_avg_ms * 1e-3) / 1e12
+    alg_bytes_launch = B * T * (8 + 4 * E)                           # one tower = one doc per rating, reference storage
     line = {
         "metric": METRIC, "value": value, "unit": "ratings/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -337,17 +367,23 @@ def run_b200(args):
         "data": "synthetic",
         "config": {"workload": "DeepCoNN E=300 F=100 T=1000 L=10 V=50001 U=1M I=100k (BASELINE configs[1])",
                    "batch_per_gpu": B, "global_batch": B * world, "conv_mode": args.conv_mode, "dropout": hp["dropout"],
-                   "parallelism": "dp%d (replicated frozen word table, dense-grad all-reduce)" % world if world > 1 else "single GPU",
+                   "parallelism": parallelism,
                    "l2_policy": "inputs larger than L2: %d resident batches x %.0f MB cycled" % (pool_n, per_batch / 2 ** 20),
                    "step": "CUDA graph of zero_grad+forward+MSE+backward+Adam"},
         "e2e": {"value": e2e_value, "unit": "ratings/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms / K, "wall_ms_per_step": float(t[1].item()) / K},
         "gpu_launches": launches_per_step * K,
-        "roofline": {"kernel": "conv_pool_tc_kernel (fused word gather + TextCNN conv + ReLU + max-pool)", "bound": "hbm",
-                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
-                     "peak_kind": peak_kind, "ms_per_launch": conv_avg_ms, "launches_per_step": 2,
+        "roofline": {"kernel": "conv_pool_tc_kernel (fused word gather + TextCNN conv + ReLU + max-pool), tcgen05 cta_group::2",
+                     "bound": "tensor", "achieved": tflops, "peak": tf_peak, "unit": "TFLOP/s", "frac": tflops / tf_peak,
+                     "traffic": NCU_CONV_DRAM_BYTES_PER_LAUNCH if (B == 4096 and world == 1) else None,
+                     "peak_kind": peak_kind + " (cuBLAS bf16, sustained)", "ms_per_launch": conv_avg_ms, "launches_per_step": 2,
                      "share_of_step": 2 * conv_avg_ms / step_ms, "timing": timing,
-                     "tensor_tflops": tflops, "tensor_peak": tf_peak, "tensor_frac": tflops / tf_peak},
+                     "executed_flops_per_launch": exec_flops, "mean_informative_rows_per_doc": positions_per_launch / B - 2,
+                     "algorithmic_flops_per_launch": alg_flops, "algorithmic_tflops": alg_flops / (conv_avg_ms * 1e-3) / 1e12,
+                     "algorithmic_bytes_per_launch": alg_bytes_launch,
+                     "algorithmic_gbs": alg_bytes_launch / (conv_avg_ms * 1e-3) / 1e9,
+                     "note": "achieved = executed FLOPs (exact padding-run shortcut applied) / event time; "
+                             "algorithmic_* = the reference's dense work (all T+2 positions, fp32 rows + int64 ids) / the same time"},
         "step_roofline": {"bytes_per_rating": algorithmic_bytes_per_rating(hp),
                           "achieved_gbs": algorithmic_bytes_per_rating(hp) * value / world / 1e9,
                           "frac_of_hbm_peak": algorithmic_bytes_per_rating(hp) * value / world / 1e9 / hbm_peak},
@@ -362,19 +398,32 @@ def run_b200(args):
         line["cpu_baseline"] = {"value": rate, "unit": "ratings/s", "cores": cores, "kind": "port",
                                 "sample": "%d timed steps of %d ratings (same synthetic workload), oracle/r4r_oracle.py::train_batches" % (steps, REF_SAMPLE_B)}
     print(json.dumps(line), flush=True)
+    _finish(world)
+
+
+def _finish(world):
+    """Multi-rank runs leave without tearing NCCL / symmetric memory down: the captured graphs still hold
+    communicator work and ProcessGroupNCCL's destructor can block on it."""
     if world > 1:
-        dist.destroy_process_group()
+        import torch
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=HP["batch_size"], help="ratings per GPU per step")
     ap.add_argument("--conv-mode", default="f16", choices=["f16", "bf16", "exact"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--table", default="sharded", choices=["sharded", "replicated"], help="word table placement for --gpus > 1")
+    ap.add_argument("--force-shard", action="store_true", help="run the sharded-table path at world size 1 (measures its device-side cost)")
+    ap.add_argument("--transport", default="nccl", choices=["nccl", "p2p"], help="how sharded word rows travel")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

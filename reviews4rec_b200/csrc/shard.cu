@@ -20,13 +20,60 @@
 namespace {
 constexpr int THREADS = 256;
 
-// ---- word-table plan, step 1: presence flags of the token ids of this rank's documents
-__global__ void __launch_bounds__(THREADS) shard_mark_kernel(const int64_t* __restrict__ idx, int64_t n, int64_t V,
-                                                             int32_t* __restrict__ flags) {
-  for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS) {
-    const int64_t id = __ldg(idx + i);
-    if (id < 0 || id >= V) __trap();                  // the reference device-asserts on OOB ids
-    if (flags[id] == 0) flags[id] = 1;                // benign race: every writer stores the same value
+// ---- word-table plan, step 1: presence flags of the token ids of this rank's documents.
+// Padding makes ~60 % of all tokens the SAME id and the rest is Zipfian, so marking flags[id]
+// directly would queue millions of accesses on a handful of L2 sectors (each SM keeps a stale 0 in
+// its L1).  Every CTA therefore collects the ids it sees in a shared-memory bitmap first (ids below
+// MARK_BITS; a lane also skips an id equal to its left neighbour's or to the one it handled last) and
+// publishes the set bits once at the end: at most one global access per (CTA, distinct id).
+constexpr int MARK_THREADS = 512;
+constexpr int64_t MARK_BITS = 1 << 20;               // 128 KB of shared memory covers ids < 1,048,576
+
+__device__ __forceinline__ void mark_global(int32_t* flags, int64_t id) {
+  if (__ldcg(flags + id) == 0) flags[id] = 1;        // benign race: every writer stores 1
+}
+
+__global__ void __launch_bounds__(MARK_THREADS) shard_mark_kernel(const int64_t* __restrict__ idx, int64_t n, int64_t V,
+                                                                  int32_t* __restrict__ flags, int64_t bits) {
+  extern __shared__ uint32_t bitmap[];               // bits / 32 words
+  const int words = (int)((bits + 31) >> 5);
+  for (int w = threadIdx.x; w < words; w += MARK_THREADS) bitmap[w] = 0u;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  constexpr int U = 4;                                 // ids per lane per trip: four independent loads in flight
+  const int64_t stride = (int64_t)gridDim.x * MARK_THREADS * U;
+  int64_t mine = -1;                                   // the id this lane handled last
+  for (int64_t i0 = ((int64_t)blockIdx.x * MARK_THREADS + (threadIdx.x & ~31)) * U; i0 < n; i0 += stride) {   // warp-uniform trip count
+    int64_t id[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * 32 + lane;
+      id[u] = i < n ? __ldg(idx + i) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (id[u] >= V) __trap();                        // the reference device-asserts on OOB ids
+      if (id[u] < -1) __trap();
+      const int64_t left = __shfl_up_sync(0xffffffffu, id[u], 1);
+      if (id[u] >= 0 && id[u] != mine && (lane == 0 || id[u] != left)) {
+        mine = id[u];
+        if (id[u] < bits) {
+          const uint32_t m = 1u << (id[u] & 31);
+          if ((bitmap[id[u] >> 5] & m) == 0u) atomicOr(&bitmap[id[u] >> 5], m);
+        } else {
+          mark_global(flags, id[u]);                   // beyond the bitmap: rare ids of a very large vocabulary
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int w = threadIdx.x; w < words; w += MARK_THREADS) {
+    uint32_t b = bitmap[w];
+    while (b) {
+      const int k = __ffs(b) - 1;
+      b &= b - 1;
+      mark_global(flags, (int64_t)w * 32 + k);
+    }
   }
 }
 
@@ -185,7 +232,19 @@ extern "C" int r4r_shard_mark(const int64_t* idx, int64_t n, int64_t V, int32_t*
   R4R_REQUIRE(idx && flags, R4R_EINVAL, "shard_mark: null pointer");
   R4R_REQUIRE(n >= 0 && V > 0, R4R_EINVAL, "shard_mark: bad sizes");
   if (n == 0) return 0;
-  shard_mark_kernel<<<grid_of(n, THREADS * 4), THREADS, 0, as_stream(stream)>>>(idx, n, V, flags);
+  const int64_t bits = V < MARK_BITS ? V : MARK_BITS;
+  const size_t smem = (size_t)((bits + 31) / 32) * sizeof(uint32_t);
+  static bool attr_set = false;
+  if (!attr_set) {
+    R4R_CUDA(cudaFuncSetAttribute(shard_mark_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MARK_BITS / 8)));
+    attr_set = true;
+  }
+  // few, fat CTAs: every CTA publishes its own bitmap, so their number bounds the global flag traffic
+  int64_t blocks = cdiv64(n, MARK_THREADS * 16);
+  const int64_t cap_blocks = smem > 48 * 1024 ? 148 : 148 * 2;
+  if (blocks > cap_blocks) blocks = cap_blocks;
+  if (blocks < 1) blocks = 1;
+  shard_mark_kernel<<<(unsigned)blocks, MARK_THREADS, smem, as_stream(stream)>>>(idx, n, V, flags, bits);
   R4R_CHECK_LAUNCH("shard_mark");
   return 0;
 }

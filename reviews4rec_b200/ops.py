@@ -24,6 +24,24 @@ def set_doc_plan(on: bool) -> None:
     _doc_plan = bool(on)
 
 
+def get_doc_plan() -> bool:
+    return _doc_plan
+
+
+def doc_lengths(idx: "torch.Tensor") -> "torch.Tensor":
+    """Informative prefix length of every document of ``idx`` [N,T] (r4r_doc_plan): rows after it repeat
+    one token and cannot change the max-pooled features."""
+    _need_cuda(idx)
+    idx = _i64c(idx)
+    N, T = idx.shape
+    doc_len = torch.empty(N, device=idx.device, dtype=torch.int32)
+    order = torch.empty(N, device=idx.device, dtype=torch.int32)
+    ws = torch.empty(_lib.lib.r4r_doc_plan_ws_bytes(), device=idx.device, dtype=torch.uint8)
+    if N:
+        call("r4r_doc_plan", _p(idx), N, T, _p(doc_len), _p(order), _p(ws), _stream())
+    return doc_len
+
+
 def set_conv_mode(mode: str) -> None:
     """'exact' = fp32 CUDA-core kernel (strict parity); 'f16' / 'bf16' = tcgen05 tensor-core kernel
     reading a private half-precision shadow of the frozen word table (fp32 accumulation)."""
@@ -125,23 +143,45 @@ class ShadowTable:
         return self.tensor
 
 
+class PrebuiltShadow:
+    """Half-precision word rows that already are in the conv kernel's layout ([V+1, Epad], row V zero):
+    the per-step row cache a sharded word table receives from the owners (sharded.py).  There is no
+    fp32 table behind it; ``conv_pool`` is then called with ``table=None``."""
+
+    def __init__(self, tensor: torch.Tensor, V: int, E: int, mode: str):
+        self.tensor, self.V, self.E, self.mode = tensor, int(V), int(E), mode
+        self.epad = int(tensor.shape[1])
+
+    def get(self, table, mode):
+        if mode != self.mode:
+            raise RuntimeError("word rows were fetched for conv mode %r, not %r" % (self.mode, mode))
+        return self.tensor
+
+
 # ------------------------------------------------------------------------------------ conv + pool
 def conv_pool_forward(idx: torch.Tensor, table: torch.Tensor, conv_w: torch.Tensor, conv_b: torch.Tensor,
                       mode: str, shadow: Optional[ShadowTable] = None, want_shadow: bool = False):
     """Fused gather -> conv(3xE, pad 2) -> relu -> global max-pool.  Returns (pooled [N,F], argmax [N,F])
     (+ the half-precision shadow rows it read, (tensor, Epad) or None, when ``want_shadow``)."""
     _need_cuda(idx, table, conv_w, conv_b)
-    idx, table, conv_w, conv_b = _i64c(idx), _f32c(table), _f32c(conv_w), _f32c(conv_b)
+    idx, conv_w, conv_b = _i64c(idx), _f32c(conv_w), _f32c(conv_b)
     N, T = idx.shape
-    V, E = table.shape
+    if table is None:
+        if not isinstance(shadow, PrebuiltShadow) or mode == "exact":
+            raise RuntimeError("conv_pool needs the fp32 word table (or prebuilt half-precision rows in f16/bf16 mode)")
+        V, E = shadow.V, shadow.E
+    else:
+        table = _f32c(table)
+        V, E = table.shape
+    dev = idx.device
     F = conv_w.shape[0]
     if tuple(conv_w.shape) != (F, 1, 3, E):
         raise RuntimeError("conv weight must be [F,1,3,%d] (window size 3), got %s" % (E, tuple(conv_w.shape)))
-    pooled = torch.empty(N, F, device=table.device, dtype=torch.float32)
-    argmax = torch.empty(N, F, device=table.device, dtype=torch.int32)
+    pooled = torch.empty(N, F, device=dev, dtype=torch.float32)
+    argmax = torch.empty(N, F, device=dev, dtype=torch.int32)
     used = None
     if mode == "exact":
-        keys = torch.empty(N, F, device=table.device, dtype=torch.int64)
+        keys = torch.empty(N, F, device=dev, dtype=torch.int64)
         with _ConvTimer():
             call("r4r_conv_pool_simt", _p(table), V, E, _p(idx), N, T, _p(conv_w), _p(conv_b), F,
                  _p(pooled), _p(argmax), _p(keys), _stream())
@@ -152,27 +192,27 @@ def conv_pool_forward(idx: torch.Tensor, table: torch.Tensor, conv_w: torch.Tens
         nbytes = _lib.lib.r4r_conv_wpack_bytes(E, F)
         if nbytes <= 0:
             raise RuntimeError("conv_pool_tc: unsupported shape E=%d F=%d" % (E, F))
-        wpack = torch.empty(nbytes, device=table.device, dtype=torch.uint8)
+        wpack = torch.empty(nbytes, device=dev, dtype=torch.uint8)
         call("r4r_conv_pack_weights", _p(conv_w), E, F, _p(wpack), dt, _stream())
         doc_len = doc_order = None
         if _doc_plan and T + 2 > _PAIR_TILE and N > 0:
             # documents padded with a repeated token are cut to their informative prefix (exact, see
             # r4r_doc_plan in include/r4r_b200.h) and issued longest first
-            doc_len = torch.empty(N, device=table.device, dtype=torch.int32)
-            doc_order = torch.empty(N, device=table.device, dtype=torch.int32)
-            ws = torch.empty(_lib.lib.r4r_doc_plan_ws_bytes(), device=table.device, dtype=torch.uint8)
+            doc_len = torch.empty(N, device=dev, dtype=torch.int32)
+            doc_order = torch.empty(N, device=dev, dtype=torch.int32)
+            ws = torch.empty(_lib.lib.r4r_doc_plan_ws_bytes(), device=dev, dtype=torch.uint8)
             call("r4r_doc_plan", _p(idx), N, T, _p(doc_len), _p(doc_order), _p(ws), _stream())
         with _ConvTimer():
             call("r4r_conv_pool_tc", _p(sh), V, shadow.epad, E, dt, _p(idx), N, T, _p(wpack), _p(conv_b), F,
                  _p(pooled), _p(argmax), _p(doc_len), _p(doc_order), _stream())
-        used = (sh, shadow.epad)
+        used = (sh, shadow.epad, V)
     return (pooled, argmax, used) if want_shadow else (pooled, argmax)
 
 
 class _ConvPool(torch.autograd.Function):
     @staticmethod
     def forward(ctx, idx, table, conv_w, conv_b, mode, shadow):
-        if table.requires_grad:
+        if table is not None and table.requires_grad:
             raise RuntimeError("the word table is frozen in the reference (DeepCoNN.py:15 freeze=True); "
                                "a trainable word table is not part of this path")
         pooled, argmax, used = conv_pool_forward(idx, table, conv_w, conv_b, mode, shadow, want_shadow=True)
@@ -187,15 +227,15 @@ class _ConvPool(torch.autograd.Function):
         idx, table, argmax, pooled = ctx.saved_tensors
         F, _, _, E = ctx.wshape
         N, T = idx.shape
-        dW = torch.zeros(ctx.wshape, device=table.device, dtype=torch.float32)
-        db = torch.zeros(F, device=table.device, dtype=torch.float32)
+        dW = torch.zeros(ctx.wshape, device=idx.device, dtype=torch.float32)
+        db = torch.zeros(F, device=idx.device, dtype=torch.float32)
         if ctx.used is None:
             call("r4r_conv_wgrad_argmax", _p(table), table.shape[0], E, _p(idx), N, T, _p(argmax), _p(pooled),
                  _p(_f32c(gpooled)), F, _p(dW), _p(db), _stream())
         else:
             # f16 / bf16 modes: gradient of what the tensor-core forward computed, from the same shadow rows
-            sh, epad = ctx.used
-            call("r4r_conv_wgrad_argmax_h", _p(sh), table.shape[0], epad, E,
+            sh, epad, V = ctx.used
+            call("r4r_conv_wgrad_argmax_h", _p(sh), V, epad, E,
                  _lib.R4R_DT_F16 if ctx.mode == "f16" else _lib.R4R_DT_BF16, _p(idx), N, T, _p(argmax), _p(pooled),
                  _p(_f32c(gpooled)), F, _p(dW), _p(db), _stream())
         return None, None, dW, db, None, None
@@ -322,5 +362,10 @@ class _RowsGather(torch.autograd.Function):
 
 
 def rows_gather(table, ids):
-    """table[ids] for an id-embedding matrix [R,L] or a bias vector [R]."""
+    """table[ids] for an id-embedding matrix [R,L] or a bias vector [R].  A parameter that
+    ``sharded.shard_model`` reduced to this rank's rows is looked up across the ranks."""
+    if hasattr(table, "_r4r_shard"):
+        from .sharded import sharded_rows_gather
+        _need_cuda(table, ids)
+        return sharded_rows_gather(table, _i64c(ids))
     return _RowsGather.apply(table, ids)

@@ -28,8 +28,9 @@ class DeepCoNN(nn.Module):
         _, _, _, user_reviews, item_reviews, user_id, item_id = data
         final_shape = tuple(user_id.shape)                      # [B] or [B,n] (ranking, eval.py:64-92)
         first_dim = user_id.numel()
-        user = self.user_conv(self.word2vec(user_reviews.reshape(first_dim, -1)))
-        item = self.item_conv(self.word2vec(item_reviews.reshape(first_dim, -1)))
+        user_docs, item_docs = self.word2vec.many(user_reviews.reshape(first_dim, -1), item_reviews.reshape(first_dim, -1))
+        user = self.user_conv(user_docs)
+        item = self.item_conv(item_docs)
         cat = torch.cat([user, item], dim=-1)
         if self.hyper_params["model_type"] == "deepconn":
             return (self.global_bias + self.fm(cat)[:, 0]).view(final_shape)

@@ -46,8 +46,9 @@ class NARRE(nn.Module):
         ub = ops.rows_gather(self.user_bias, user_id)
         ib = ops.rows_gather(self.item_bias, item_id)
         # every review is its own conv document: [n*R, W] token ids (NARRE.py:91-104)
-        user = self.user_conv(self.word2vec(user_reviews.reshape(n * R_u, W_u))).view(n, R_u, -1)
-        item = self.item_conv(self.word2vec(item_reviews.reshape(n * R_i, W_i))).view(n, R_i, -1)
+        user_docs, item_docs = self.word2vec.many(user_reviews.reshape(n * R_u, W_u), item_reviews.reshape(n * R_i, W_i))
+        user = self.user_conv(user_docs).view(n, R_u, -1)
+        item = self.item_conv(item_docs).view(n, R_i, -1)
         user = self.attention(user, self.item_embedding(reviewed_items), self.attention_scorer_user)
         item = self.attention(item, self.user_embedding(users_who_reviewed), self.attention_scorer_item)
         user = user + self.dropout(self.user_embedding(user_id))

@@ -63,9 +63,8 @@ class TransNet(nn.Module):
         this_reviews, _, _, user_reviews, item_reviews, user_id, item_id = data
         final_shape = tuple(user_id.shape)
         n = user_id.numel()
-        user = self.target.embed(user_reviews.reshape(n, -1))
-        item = self.target.embed(item_reviews.reshape(n, -1))
-        this = self.target.embed(this_reviews.reshape(n, -1))
+        user, item, this = self.target.word2vec.many(user_reviews.reshape(n, -1), item_reviews.reshape(n, -1),
+                                                     this_reviews.reshape(n, -1))
         self.source(user, item)
         if self.hyper_params["model_type"] == "transnet++":
             u = self.dropout(self.user_embedding(user_id.reshape(-1)))

@@ -34,6 +34,10 @@ class WordTable(nn.Embedding):
     def forward(self, idx):
         return Docs(idx, self.weight, self._shadow)
 
+    def many(self, *idx_list):
+        """All word lookups of one step at once (a single exchange when the table is sharded)."""
+        return tuple(self.forward(i) for i in idx_list)
+
     def materialize(self, idx):
         return ops.word_gather(self.weight, idx)
 

@@ -91,8 +91,6 @@ class CapturedStep:
     """
 
     def __init__(self, model, criterion, optimizer, data, y, se_sum=None, group=None, grad_div=1.0):
-        import torch.distributed as dist
-
         self.model, self.data, self.y = model, data, y
         dev = y.device
         self.se_sum = se_sum if se_sum is not None else torch.zeros(1, device=dev, dtype=torch.float32)
@@ -109,15 +107,10 @@ class CapturedStep:
             self.se_sum += se.detach().sum()
             torch.mean(se).backward()
             if group is not None:
-                grads = [p.grad for p in model.parameters() if p.grad is not None]
-                flat = torch.cat([g.reshape(-1) for g in grads])
-                dist.all_reduce(flat, group=group)
-                if grad_div != 1.0:
-                    flat /= grad_div
-                ofs = 0
-                for g in grads:
-                    g.copy_(flat[ofs:ofs + g.numel()].view_as(g))
-                    ofs += g.numel()
+                # replicated parameters: mean over ranks; row-sharded tables already received their
+                # rows' gradients from every rank inside the backward (sharded.py)
+                from .sharded import allreduce_dense_grads
+                allreduce_dense_grads(model, group, int(grad_div))
             optimizer.step()
         self.out = out
 
