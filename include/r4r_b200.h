@@ -46,6 +46,12 @@ int         r4r_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t
 int r4r_word_gather_f32(const float* table, int64_t V, int E, const int64_t* idx, int64_t n,
                         float* out, void* stream);
 
+/* Ragged -> padded documents: out[n, t] = tokens[offsets[n] + t] for t < offsets[n+1] - offsets[n], else
+ * pad_id.  Rebuilds on the device the [N, T] int64 tensors the reference's fast reader ships padded from
+ * host RAM (data_fast.py:99-109); the host side keeps only the tokens before the trailing padding run. */
+int r4r_docs_expand(const int32_t* tokens, const int64_t* offsets, int64_t N, int T, int64_t pad_id, int64_t* out,
+                    void* stream);
+
 /* Private reduced-precision copy of the frozen word table (SURVEY.md finding 2):
  * shadow[v, 0:E] = cvt(table[v,:]), shadow[v, E:Epad] = 0.  Epad % 8 == 0, row stride = Epad.
  * `shadow` holds V+1 rows: row V is all zero (r4r_conv_pool_tc reads the conv's zero padding from it). */

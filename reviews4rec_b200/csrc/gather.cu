@@ -143,3 +143,35 @@ extern "C" int r4r_rows_scatter_add(const float* gout, const int64_t* ids, int64
   R4R_CHECK_LAUNCH("rows_scatter_add");
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// Ragged -> padded documents.  The reference's fast reader keeps every rating's documents padded to
+// input_length as int64 in host RAM and ships 24 KB per rating to the device each batch
+// (data_fast.py:32-44,99-109; layout written by make_quick_data.py:21-44).  Our reader keeps only the
+// tokens before the trailing padding run as int32 (reviews4rec_b200/readers.py), copies those, and this
+// kernel rebuilds the exact [N, T] int64 tensor the models consume: out[n, t] = tokens[off[n] + t] for
+// t < off[n+1] - off[n], else pad_id.
+__global__ void __launch_bounds__(256) docs_expand_kernel(const int32_t* __restrict__ tokens, const int64_t* __restrict__ offsets,
+                                                          int64_t N, int T, int64_t pad_id, int64_t* __restrict__ out) {
+  const int64_t total = N * (int64_t)T;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / T;
+    const int t = (int)(i - n * T);
+    const int64_t lo = __ldg(offsets + n), hi = __ldg(offsets + n + 1);
+    if (hi < lo || hi - lo > T) __trap();
+    out[i] = t < hi - lo ? (int64_t)__ldg(tokens + lo + t) : pad_id;
+  }
+}
+
+extern "C" int r4r_docs_expand(const int32_t* tokens, const int64_t* offsets, int64_t N, int T, int64_t pad_id, int64_t* out,
+                               void* stream) {
+  R4R_REQUIRE(offsets && out, R4R_EINVAL, "docs_expand: null pointer");
+  R4R_REQUIRE(N >= 0 && T > 0, R4R_EINVAL, "docs_expand: bad sizes");
+  if (N == 0) return 0;
+  R4R_REQUIRE(tokens, R4R_EINVAL, "docs_expand: null token pointer");
+  int64_t blocks = cdiv64(N * (int64_t)T, 256 * 4);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  docs_expand_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(tokens, offsets, N, T, pad_id, out);
+  R4R_CHECK_LAUNCH("docs_expand");
+  return 0;
+}

@@ -1,0 +1,178 @@
+"""B200-side counterpart of the reference's fast reader (data_fast.py:14-123).
+
+The reference keeps the eight HDF5 datasets ``a..h`` of a split (make_quick_data.py:21-44: ``a`` this
+review, ``b`` users who reviewed the item, ``c`` items the user reviewed, ``d`` user document, ``e`` item
+document, ``f`` user id, ``g`` item id -- all int64 -- and ``h`` the rating) fully padded in host RAM and
+turns a slice of each into a device ``LongTensor`` per batch (data_fast.py:99-109): 24 KB per rating cross
+PCIe although ~60 % of every document is the padding token.
+
+``RaggedReader`` takes the same arrays, keeps each document as int32 tokens up to its trailing padding run
+(pinned host memory), copies only those per batch and rebuilds the identical padded int64 tensors on the
+device (``r4r_docs_expand``), so the models see exactly what the reference's reader would have produced.
+It honours the reader protocol ``train()`` / ``evaluate()`` use: ``iter(eval=False)`` yielding
+``([a, b, c, d, e, f, g], h)``, ``len(reader)`` = number of batches, a short last batch.
+"""
+import ctypes
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from ._lib import call
+
+PAD_ID = 0          # data.py:198-199 pads documents with token 0
+
+
+def _vp(t):
+    return ctypes.c_void_p(t.data_ptr() if t is not None else 0)
+
+
+class RaggedDocs:
+    """One padded document array ``[N, T]`` or ``[N, R, W]`` (NARRE: every review is its own padded row)
+    stored as int32 tokens + int64 row offsets in (pinned) host memory."""
+
+    def __init__(self, padded, pad_id: int = PAD_ID, pin: bool = True):
+        arr = np.ascontiguousarray(np.asarray(padded))
+        if arr.ndim < 2:
+            raise ValueError("documents must be [N, T] or [N, R, W]")
+        self.tail = tuple(arr.shape[1:])                    # per-rating shape
+        self.T = int(arr.shape[-1])
+        self.rows_per_item = int(np.prod(arr.shape[1:-1])) if arr.ndim > 2 else 1
+        flat = arr.reshape(-1, self.T)
+        if flat.size and (flat.min() < 0 or flat.max() >= 2 ** 31):
+            raise ValueError("token ids must fit in int32")
+        keep = flat != pad_id
+        # length = index after the last non-pad token (interior pad tokens are ordinary tokens)
+        lens = np.where(keep.any(axis=1), self.T - np.argmax(keep[:, ::-1], axis=1), 0).astype(np.int64)
+        mask = np.arange(self.T)[None, :] < lens[:, None]
+        tokens = torch.from_numpy(flat[mask].astype(np.int32))
+        offsets = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)]).astype(np.int64))
+        self.pad_id = int(pad_id)
+        self.tokens = tokens.pin_memory() if (pin and torch.cuda.is_available()) else tokens
+        self.offsets = offsets                               # [rows + 1]; sliced + rebased per batch
+        self.n_items = int(arr.shape[0])
+
+    def batch_host(self, lo: int, hi: int, off_out=None):
+        """(tokens int32 view, offsets int64 [rows+1] rebased to 0) of ratings lo..hi-1; the rebased
+        offsets are written into ``off_out`` (a pinned staging buffer) when given."""
+        r0, r1 = lo * self.rows_per_item, hi * self.rows_per_item
+        o = self.offsets[r0:r1 + 1]
+        base = int(o[0])
+        if off_out is None:
+            reb = o - base
+        else:
+            reb = torch.sub(o, base, out=off_out[: o.numel()])
+        return self.tokens[base:int(o[-1])], reb
+
+    def max_batch_tokens(self, bsz: int) -> int:
+        rows = bsz * self.rows_per_item
+        o = self.offsets
+        if o.numel() - 1 <= rows:
+            return int(o[-1])
+        return int((o[rows:] - o[:-rows]).max())            # batches start at multiples of bsz, this bound holds for any start
+
+    def to_padded(self, tokens, offsets):
+        """Host-side inverse (tests): numpy padded array from a ragged slice."""
+        rows = offsets.numel() - 1
+        out = np.full((rows, self.T), self.pad_id, dtype=np.int64)
+        t, o = tokens.numpy(), offsets.numpy()
+        for r in range(rows):
+            out[r, : o[r + 1] - o[r]] = t[o[r]:o[r + 1]]
+        return out.reshape((-1,) + self.tail)
+
+
+class _Slot:
+    """Device staging of one batch: ragged token buffers and the padded tensors the model reads."""
+
+    def __init__(self, reader, device):
+        bsz = reader.bsz
+        self.tok, self.off, self.off_host, self.pad = {}, {}, {}, {}
+        self.used = False
+        for k, rd in reader.docs.items():
+            rows = bsz * rd.rows_per_item
+            self.tok[k] = torch.empty(max(1, rd.max_batch_tokens(bsz)), device=device, dtype=torch.int32)
+            self.off[k] = torch.empty(rows + 1, device=device, dtype=torch.int64)
+            self.off_host[k] = torch.empty(rows + 1, dtype=torch.int64).pin_memory()
+            self.pad[k] = torch.empty((bsz,) + rd.tail, device=device, dtype=torch.int64)
+        self.small = {k: torch.empty((bsz,) + tuple(v.shape[1:]), device=device, dtype=v.dtype) for k, v in reader.small.items()}
+
+
+class RaggedReader:
+    DOC_KEYS = ("a", "d", "e")                               # this review, user document, item document
+    SMALL_KEYS = ("b", "c", "f", "g", "h")
+
+    def __init__(self, hyper_params: dict, arrays: Dict[str, Optional[np.ndarray]], device, slots: int = 2):
+        """``arrays``: the datasets ``a..h`` of one split as numpy arrays (``None`` for slots the model
+        does not read, as ``iter_simple`` does for MF: data.py:350-358)."""
+        self.hyper_params = hyper_params
+        self.bsz = int(hyper_params["batch_size"])
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("RaggedReader stages batches on a CUDA device (no CPU fallback)")
+        self.total = int(len(arrays["h"]))
+        self.docs = {k: RaggedDocs(arrays[k]) for k in self.DOC_KEYS if arrays.get(k) is not None}
+        self.small = {}
+        for k in self.SMALL_KEYS:
+            if arrays.get(k) is not None:
+                t = torch.from_numpy(np.ascontiguousarray(arrays[k]))
+                t = t.float() if k == "h" else t.long()      # FloatTensor(h), LongTensor(rest): data_fast.py:102-109
+                self.small[k] = t.pin_memory()
+        self.slots = [_Slot(self, self.device) for _ in range(slots)]
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._free = [torch.cuda.Event() for _ in range(slots)]
+        self._ready = [torch.cuda.Event() for _ in range(slots)]
+        self.h2d_bytes_last = 0
+
+    def __len__(self):
+        return self.total // self.bsz + int(self.total % self.bsz > 0)
+
+    def stage(self, batch: int, slot: int):
+        """Enqueue on the copy stream: H2D of batch ``batch``'s ragged tokens / offsets / ids / ratings and
+        the expansion into slot ``slot``'s padded tensors.  Returns (data, y, n_ratings); consumers must
+        ``wait_ready(slot)`` first and ``release(slot)`` after their last use."""
+        lo = (batch % len(self)) * self.bsz
+        hi = min(self.total, lo + self.bsz)
+        n = hi - lo
+        S = self.slots[slot]
+        nbytes = 0
+        if S.used:
+            self._ready[slot].synchronize()                  # the previous copies out of this slot's pinned staging are done
+        S.used = True
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self._free[slot])
+            for k, rd in self.docs.items():
+                tok, off = rd.batch_host(lo, hi, S.off_host[k])
+                S.tok[k][: tok.numel()].copy_(tok, non_blocking=True)
+                S.off[k][: off.numel()].copy_(off, non_blocking=True)
+                nbytes += tok.numel() * 4 + off.numel() * 8
+                call("r4r_docs_expand", _vp(S.tok[k]), _vp(S.off[k]), n * rd.rows_per_item, rd.T, rd.pad_id, _vp(S.pad[k]),
+                     ctypes.c_void_p(self.copy_stream.cuda_stream))
+            for k, v in self.small.items():
+                S.small[k][:n].copy_(v[lo:hi], non_blocking=True)
+                nbytes += (hi - lo) * v[0].numel() * v.element_size()
+            self._ready[slot].record(self.copy_stream)
+        self.h2d_bytes_last = nbytes
+        get = lambda d, k: d[k][:n] if k in d else None
+        data = [get(S.pad, "a"), get(S.small, "b"), get(S.small, "c"), get(S.pad, "d"), get(S.pad, "e"),
+                get(S.small, "f"), get(S.small, "g")]
+        return data, S.small["h"][:n], n
+
+    def wait_ready(self, slot: int, stream=None):
+        (stream or torch.cuda.current_stream()).wait_event(self._ready[slot])
+
+    def release(self, slot: int, stream=None):
+        self._free[slot].record(stream or torch.cuda.current_stream())
+
+    def iter(self, eval=False):
+        """Reader protocol of main.train / eval.evaluate.  Batch k+1 is staged while batch k is consumed."""
+        nb, ns = len(self), len(self.slots)
+        if nb == 0:
+            return
+        nxt = self.stage(0, 0)
+        for b in range(nb):
+            cur, slot = nxt, b % ns
+            if b + 1 < nb:
+                nxt = self.stage(b + 1, (b + 1) % ns)
+            self.wait_ready(slot)
+            yield cur[0], cur[1]
+            self.release(slot)
