@@ -218,18 +218,48 @@ def run_b200(args):
     criterion = MSELoss(hp)
     opt = FusedAdam(model.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"], capturable=True)
 
-    # resident pool: POOL batches x (2 docs x B x T x 8 B); > L2 (126 MB) so inputs are cold every step
-    per_batch = 2 * B * hp["input_length"] * 8
-    pool_n = max(2, min(8, -(-160 * 2 ** 20 // per_batch)))
-    res = SyntheticReader(hp, B, pool_n, V_WORDS, seed=1234, device=dev, rank=rank)
-    host = SyntheticReader(hp, B, pool_n, V_WORDS, seed=4321, device=None, pin=True, rank=rank)
+    # ---- synthetic split, generated once on the host (numpy, seeded), as the eight arrays a..h of the reference's
+    # quick-data format (make_quick_data.py:21-44); RaggedReader keeps it in pinned host memory
+    import numpy as np
+    from reviews4rec_b200.readers import RaggedReader
+    T = hp["input_length"]
+    ragged = args.docs == "ragged"
+    # resident pool larger than L2 (126 MB): padded int64 batches are 2*B*T*8 B; ragged ones ~0.2x that
+    per_batch = 2 * B * T * 8 * (0.21 if ragged else 1.0)
+    pool_n = max(2, min(12, -(-160 * 2 ** 20 // int(per_batch))))
+    host = SyntheticReader(hp, B, pool_n, V_WORDS, seed=1234, device=None, pin=False, rank=rank)
+    cat = lambda j: np.concatenate([b_[0][j].numpy() for b_ in host.batches])
+    arrays = {k: None for k in "abcdefgh"}
+    arrays.update(d=cat(3), e=cat(4), f=cat(5), g=cat(6), h=np.concatenate([b_[1].numpy() for b_ in host.batches]))
+    # the reader always hands ops.RaggedIdx documents over; --docs decides whether the kernels read them directly
+    # ("ragged") or rebuild the padded int64 ids inside the captured step first ("padded", r4r_docs_expand)
+    ops.set_ragged_native(ragged)
+    rr = RaggedReader(hp, arrays, dev, native=True)
+
+    # ---- device-resident copies of every batch (the `value` measurement reads these)
+    class _Res:
+        batches = []
+    res = _Res()
+    resident_bytes = 0
+    for bi in range(pool_n):
+        hd, hy = host.batches[bi]
+        if ragged:
+            docs = []
+            for k in ("d", "e"):
+                tok, off = rr.docs[k].batch_host(bi * B, (bi + 1) * B)
+                docs.append(ops.RaggedIdx(tok.to(dev), off.to(dev), (B, T), rr.docs[k].pad_id))
+                resident_bytes += tok.numel() * 4 + off.numel() * 8
+        else:
+            docs = [hd[3].to(dev), hd[4].to(dev)]
+            resident_bytes += 2 * B * T * 8
+        res.batches.append(([None, None, None, docs[0], docs[1], hd[5].to(dev), hd[6].to(dev)], hy.to(dev)))
 
     # conv positions the launches actually process (documents cut to their informative prefix, exact)
     pos_sum = 0
     for d, _ in res.batches:
         for idx in (d[3], d[4]):
             pos_sum += int(ops.doc_lengths(idx).sum().item()) + 2 * idx.shape[0]
-    positions_per_launch = pos_sum / (2.0 * len(res.batches)) if ops.get_doc_plan() else float(B * (hp["input_length"] + 2))
+    positions_per_launch = pos_sum / (2.0 * len(res.batches)) if ops.get_doc_plan() else float(B * (T + 2))
 
     se_sum = torch.zeros(1, device=dev, dtype=torch.float32)
     conv_events = []
@@ -280,15 +310,9 @@ def run_b200(args):
     value = world * B * K / (ms_total * 1e-3)
 
     # ---- e2e through the public API: RaggedReader (this repo's counterpart of data_fast.DataLoader) holds the
-    # synthetic split in pinned HOST memory -- int32 tokens up to each document's trailing padding run -- and per
-    # step copies them H2D (copy stream, double-buffered), rebuilds the padded int64 batch on the device
-    # (r4r_docs_expand) and hands it to the captured step; the running SE sum is read back D2H every step.
-    import numpy as np
-    from reviews4rec_b200.readers import RaggedReader
-    cat = lambda j: np.concatenate([b_[0][j].numpy() for b_ in host.batches])
-    arrays = {k: None for k in "abcdefgh"}
-    arrays.update(d=cat(3), e=cat(4), f=cat(5), g=cat(6), h=np.concatenate([b_[1].numpy() for b_ in host.batches]))
-    rr = RaggedReader(hp, arrays, dev)
+    # split in pinned HOST memory -- int32 tokens up to each document's trailing padding run -- and per step copies
+    # a batch H2D (copy stream, double-buffered) into the buffers the captured step reads (as ops.RaggedIdx
+    # documents, or expanded to padded int64 with --docs padded); the running SE sum is read back D2H every step.
     main = torch.cuda.current_stream()
     se_e2e = torch.zeros(1, device=dev, dtype=torch.float32)
     steps_e2e = []
@@ -332,7 +356,17 @@ def run_b200(args):
     e2e_value = world * B * K / (e2e_ms * 1e-3)
 
     # ---- the same with the batches shipped as the reference's reader does: padded int64 [B,T] from pinned host memory
-    static = [(list(steps_e2e[s_].data), steps_e2e[s_].y) for s_ in range(2)]
+    if True:
+        pstatic = [([None, None, None] + [torch.empty(B, T, device=dev, dtype=torch.int64) for _ in range(2)]
+                    + [torch.empty(B, device=dev, dtype=torch.int64) for _ in range(2)],
+                    torch.empty(B, device=dev, dtype=torch.float32)) for _ in range(2)]
+        for (pd, py), (hd, hy) in zip(pstatic, host.batches):
+            for dst, src in zip(pd, hd):
+                if dst is not None:
+                    dst.copy_(src)
+            py.copy_(hy)
+        steps_pad = [CapturedStep(model, criterion, opt, pd, py, se_e2e, group, float(world)) for pd, py in pstatic]
+        hpin = [([None if x is None else x.pin_memory() for x in hd], hy.pin_memory()) for hd, hy in host.batches[:3]]
     copy_stream = torch.cuda.Stream()
     ready = [torch.cuda.Event() for _ in range(2)]
     done = [torch.cuda.Event() for _ in range(2)]
@@ -340,16 +374,16 @@ def run_b200(args):
     def padded_loop(n):
         for i in range(n):
             s_ = i & 1
-            hd, hy = host.batches[i % pool_n]
+            hd, hy = hpin[i % len(hpin)]
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(done[s_])
-                for dst, src in zip(static[s_][0], hd):
+                for dst, src in zip(pstatic[s_][0], hd):
                     if dst is not None:
                         dst.copy_(src, non_blocking=True)
-                static[s_][1].copy_(hy, non_blocking=True)
+                pstatic[s_][1].copy_(hy, non_blocking=True)
                 ready[s_].record(copy_stream)
             main.wait_event(ready[s_])
-            steps_e2e[s_].replay()
+            steps_pad[s_].replay()
             done[s_].record(main)
             se_host[i:i + 1].copy_(se_e2e, non_blocking=True)
 
@@ -399,13 +433,17 @@ def run_b200(args):
         "config": {"workload": "DeepCoNN E=300 F=100 T=1000 L=10 V=50001 U=1M I=100k (BASELINE configs[1])",
                    "batch_per_gpu": B, "global_batch": B * world, "conv_mode": args.conv_mode, "dropout": hp["dropout"],
                    "parallelism": parallelism,
-                   "l2_policy": "inputs larger than L2: %d resident batches x %.0f MB cycled" % (pool_n, per_batch / 2 ** 20),
+                   "documents": ("ragged on the device (ops.RaggedIdx: int32 tokens before each trailing padding run + offsets); "
+                                 "same padded documents as the reference's reader, never materialised") if ragged
+                                else "padded int64 [B,T] as the reference's reader yields them",
+                   "l2_policy": "inputs larger than L2: %d resident batches, %.0f MB in total, cycled" % (pool_n, resident_bytes / 2 ** 20),
                    "step": "CUDA graph of zero_grad+forward+MSE+backward+Adam"},
         "e2e": {"value": e2e_value, "unit": "ratings/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms / K, "wall_ms_per_step": float(t[1].item()) / K,
                 "api": "readers.RaggedReader (pinned host split: int32 tokens before each document's trailing padding run) "
-                       "-> H2D -> r4r_docs_expand -> train.CapturedStep",
-                "padded_int64_reader": {"value": pad_value, "ms_per_step": pad_ms / K, "h2d_bytes_per_step": host.bytes_per_batch(),
+                       "-> H2D -> ops.RaggedIdx -> train.CapturedStep (%s)" % (
+                           "kernels read the ragged tokens" if ragged else "r4r_docs_expand rebuilds the padded int64 ids inside the captured step"),
+                "padded_int64_reader": {"value": pad_value, "ms_per_step": pad_ms / K, "h2d_bytes_per_step": 2 * B * T * 8 + 2 * B * 8 + B * 4,
                                         "note": "batches shipped as data_fast.py does: padded int64 [B,T] per document, PCIe-bound"}},
         "gpu_launches": launches_per_step * K,
         "roofline": {"kernel": "conv_pool_tc_kernel (fused word gather + TextCNN conv + ReLU + max-pool), tcgen05 cta_group::2",
@@ -456,6 +494,8 @@ def main():
     ap.add_argument("--batch", type=int, default=HP["batch_size"], help="ratings per GPU per step")
     ap.add_argument("--conv-mode", default="f16", choices=["f16", "bf16", "exact"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--docs", default="padded", choices=["ragged", "padded"],
+                    help="how the reader hands documents to the model: padded int64 tensors rebuilt on the device (default) or ops.RaggedIdx")
     ap.add_argument("--table", default="sharded", choices=["sharded", "replicated"], help="word table placement for --gpus > 1")
     ap.add_argument("--force-shard", action="store_true", help="run the sharded-table path at world size 1 (measures its device-side cost)")
     ap.add_argument("--transport", default="nccl", choices=["nccl", "p2p"], help="how sharded word rows travel")

@@ -91,6 +91,21 @@ int64_t r4r_doc_plan_ws_bytes(void);
 int r4r_doc_plan(const int64_t* idx, int64_t N, int T, int32_t* doc_len, int32_t* doc_order, void* ws,
                  void* stream);
 
+/* Ragged documents (reviews4rec_b200/readers.py): document n = tokens[offsets[n] .. offsets[n+1]) followed by
+ * pad_id up to T rows -- the same padded document the readers build (data.py:198-202), without ever
+ * materialising it.  Identical results to the padded entry points on the expanded ids. */
+int r4r_conv_pool_tc_ragged(const void* shadow, int64_t V, int Epad, int E, int dtype,
+                            const int32_t* tokens, const int64_t* offsets, int64_t pad_id, int64_t N, int T,
+                            const void* wpack, const float* conv_b, int F,
+                            float* pooled, int32_t* argmax,
+                            const int32_t* doc_len, const int32_t* doc_order, void* stream);
+/* doc_len[n] = min(T, offsets[n+1] - offsets[n] + 3): the padding run starts where the stored tokens end */
+int r4r_doc_plan_ragged(const int64_t* offsets, int64_t N, int T, int32_t* doc_len, int32_t* doc_order, void* ws,
+                        void* stream);
+int r4r_conv_wgrad_argmax_h_ragged(const void* shadow, int64_t V, int Epad, int E, int dtype, const int32_t* tokens,
+                                   const int64_t* offsets, int64_t pad_id, int64_t N, int T, const int32_t* argmax,
+                                   const float* pooled, const float* gpooled, int F, float* dW, float* db, void* stream);
+
 /* Diagnostics: when `buf32_u64` (device, 32 x uint64) is non-NULL every later r4r_conv_pool_tc launch
  * writes the per-role cycle counters of its first CTA pair there (see conv_tc.cu); NULL turns it off. */
 int r4r_conv_debug_profile(void* buf32_u64);

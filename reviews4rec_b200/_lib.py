@@ -32,6 +32,9 @@ SIGNATURES = {
     "r4r_conv_pool_tc": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "r4r_doc_plan_ws_bytes": (c_i64, []),
     "r4r_doc_plan": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "r4r_conv_pool_tc_ragged": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "r4r_doc_plan_ragged": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "r4r_conv_wgrad_argmax_h_ragged": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
     "r4r_conv_debug_profile": (c_int, [c_vp]),
     "r4r_conv_wgrad_argmax": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
     "r4r_conv_wgrad_argmax_h": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
@@ -67,7 +70,7 @@ if lib.r4r_abi_version() != ABI_VERSION:
 
 # number of kernel launches issued through this binding (bench.py reports it as gpu_launches)
 launch_count = 0
-_LAUNCHES_PER_CALL = {"r4r_conv_pool_simt": 2, "r4r_linear_bwd": 2, "r4r_shard_bucket": 2, "r4r_doc_plan": 2}
+_LAUNCHES_PER_CALL = {"r4r_conv_pool_simt": 2, "r4r_linear_bwd": 2, "r4r_shard_bucket": 2, "r4r_doc_plan": 2, "r4r_doc_plan_ragged": 2}
 
 
 def check(rc, name="r4r"):

@@ -192,7 +192,10 @@ struct Params {
   const uint8_t* shadow;     // [V][Epad] 2-byte elements
   long long row_bytes;       // Epad * 2
   long long V;
-  const long long* idx;      // [N][T]
+  const long long* idx;      // [N][T] padded token ids, or NULL when the documents come ragged:
+  const int* tok32;          //   tokens of all documents back to back (those before each trailing padding run)
+  const long long* off;      //   [N+1] offsets into tok32; rows off[n+1]-off[n] .. T-1 of document n are pad_id
+  long long pad_id;
   long long N;
   int T;
   int Kc;                    // 16-byte chunks per window row = ceil(E/16)*2
@@ -216,6 +219,26 @@ struct Params {
 __device__ __forceinline__ void work_item(const Params& P, long long k, long long& doc, int& Td) {
   doc = P.doc_order ? (long long)__ldg(P.doc_order + k) : k;
   Td = P.doc_len ? __ldg(P.doc_len + doc) : P.T;
+}
+// producer's view of a work item: also where the document's stored tokens are (ragged input)
+struct DocRef {
+  long long doc;
+  int Td, npt;
+  long long base;            // ragged: offset of the document's first token in tok32
+  int len;                   // ragged: number of stored tokens (rows len..T-1 are pad_id)
+};
+__device__ __forceinline__ int tiles_of(int Td);
+__device__ __forceinline__ DocRef doc_ref(const Params& P, long long k) {
+  DocRef d;
+  work_item(P, k, d.doc, d.Td);
+  d.npt = tiles_of(d.Td);
+  d.base = 0;
+  d.len = 0;
+  if (P.tok32) {
+    d.base = __ldg(P.off + d.doc);
+    d.len = (int)(__ldg(P.off + d.doc + 1) - d.base);
+  }
+  return d;
 }
 __device__ __forceinline__ int tiles_of(int Td) { return (Td + 2 + 2 * TILE_M - 1) / (2 * TILE_M); }
 
@@ -395,13 +418,25 @@ __device__ __forceinline__ void producer_role(const Params& P, SharedCtl* ctl, u
   // Token ids of a tile's rows are fetched ONE TILE AHEAD into registers (unchecked, so the nine
   // loads are issued back to back and their HBM latency hides behind the current tile's slabs);
   // slot row r <-> document position pt*256 + rank*128 - 2 + r, -1 marks a zero (padding) row.
-  auto fetch = [&](long long doc, int Td, int pt, long long (&out)[ROWS_PER_THREAD]) {
-    const long long* drow = P.idx + doc * (long long)P.T;
+  auto fetch = [&](const DocRef& d, int pt, long long (&out)[ROWS_PER_THREAD]) {
+    if (P.tok32 == nullptr) {
+      const long long* drow = P.idx + d.doc * (long long)P.T;
 #pragma unroll
-    for (int k = 0; k < ROWS_PER_THREAD; ++k) {
-      const int r = r0 + 16 * k;
-      const int pos = pt * 2 * TILE_M + (int)rank * TILE_M - 2 + r;
-      out[k] = (r < TILE_M + 2 && pos >= 0 && pos < Td) ? __ldg(drow + pos) : -1LL;
+      for (int k = 0; k < ROWS_PER_THREAD; ++k) {
+        const int r = r0 + 16 * k;
+        const int pos = pt * 2 * TILE_M + (int)rank * TILE_M - 2 + r;
+        out[k] = (r < TILE_M + 2 && pos >= 0 && pos < d.Td) ? __ldg(drow + pos) : -1LL;
+      }
+    } else {
+      const int* drow = P.tok32 + d.base;
+#pragma unroll
+      for (int k = 0; k < ROWS_PER_THREAD; ++k) {
+        const int r = r0 + 16 * k;
+        const int pos = pt * 2 * TILE_M + (int)rank * TILE_M - 2 + r;
+        const bool in_doc = r < TILE_M + 2 && pos >= 0 && pos < d.Td;
+        const int t = (in_doc && pos < d.len) ? __ldg(drow + pos) : (int)P.pad_id;
+        out[k] = in_doc ? (long long)t : -1LL;
+      }
     }
   };
   // publish a slab: its copies have landed (wait_group), make them visible to the tensor cores
@@ -418,23 +453,23 @@ __device__ __forceinline__ void producer_role(const Params& P, SharedCtl* ctl, u
   long long w_empty = 0, w_group = 0, t_begin = clock64();
   uint32_t slot = 0, empty_parity = 1u;                  // parity the empty barrier shows once the slot is free
   uint32_t pending = 0;                                  // slabs issued but not yet published
-  long long wk = cluster_id, doc = 0;
-  int pt = 0, Td = 0, npt = 0;
+  // `cur` = the work item being copied, `nxt` = the one after it: its order / length / offsets are loaded
+  // a whole document ahead so that the token-id prefetch of its first tile never waits on them
+  long long wk = cluster_id;
+  int pt = 0;
+  DocRef cur_d, nxt_d;
+  cur_d.doc = nxt_d.doc = 0; cur_d.Td = nxt_d.Td = 0; cur_d.npt = nxt_d.npt = 1; cur_d.base = nxt_d.base = 0; cur_d.len = nxt_d.len = 0;
   long long cur[ROWS_PER_THREAD], nxt[ROWS_PER_THREAD];
   if (wk < P.N) {
-    work_item(P, wk, doc, Td);
-    npt = tiles_of(Td);
-    fetch(doc, Td, 0, cur);
+    cur_d = doc_ref(P, wk);
+    if (wk + nclusters < P.N) nxt_d = doc_ref(P, wk + nclusters);
+    fetch(cur_d, 0, cur);
   }
   while (wk < P.N) {
-    long long nk = wk, ndoc = doc;
-    int pt_next = pt + 1, nTd = Td, nnpt = npt;
-    if (pt_next == npt) {
-      pt_next = 0;
-      nk += nclusters;
-      if (nk < P.N) { work_item(P, nk, ndoc, nTd); nnpt = tiles_of(nTd); }
-    }
-    if (nk < P.N) fetch(ndoc, nTd, pt_next, nxt);
+    const bool wrap = pt + 1 == cur_d.npt;
+    const long long nk = wrap ? wk + nclusters : wk;
+    const int pt_next = wrap ? 0 : pt + 1;
+    if (nk < P.N) fetch(wrap ? nxt_d : cur_d, pt_next, nxt);
     const uint8_t* src[ROWS_PER_THREAD];
 #pragma unroll
     for (int k = 0; k < ROWS_PER_THREAD; ++k) {
@@ -463,7 +498,11 @@ __device__ __forceinline__ void producer_role(const Params& P, SharedCtl* ctl, u
     });
 #pragma unroll
     for (int k2 = 0; k2 < ROWS_PER_THREAD; ++k2) cur[k2] = nxt[k2];
-    wk = nk; doc = ndoc; Td = nTd; npt = nnpt;
+    if (wrap) {
+      cur_d = nxt_d;
+      if (nk + nclusters < P.N) nxt_d = doc_ref(P, nk + nclusters);   // consumed a document later
+    }
+    wk = nk;
     pt = pt_next;
   }
   cp_async_wait<0>();
@@ -665,12 +704,13 @@ extern "C" int r4r_conv_pack_weights(const float* conv_w, int E, int F, void* wp
   return 0;
 }
 
-extern "C" int r4r_conv_pool_tc(const void* shadow, int64_t V, int Epad, int E, int dtype,
-                                const int64_t* idx, int64_t N, int T,
-                                const void* wpack, const float* conv_b, int F,
-                                float* pooled, int32_t* argmax,
-                                const int32_t* doc_len, const int32_t* doc_order, void* stream) {
-  R4R_REQUIRE(shadow && idx && wpack && conv_b && pooled && argmax, R4R_EINVAL, "conv_pool_tc: null pointer");
+static int conv_pool_tc_launch(const void* shadow, int64_t V, int Epad, int E, int dtype,
+                               const int64_t* idx, const int32_t* tok32, const int64_t* off, int64_t pad_id, int64_t N, int T,
+                               const void* wpack, const float* conv_b, int F,
+                               float* pooled, int32_t* argmax,
+                               const int32_t* doc_len, const int32_t* doc_order, void* stream) {
+  R4R_REQUIRE(shadow && (idx || (tok32 && off)) && wpack && conv_b && pooled && argmax, R4R_EINVAL, "conv_pool_tc: null pointer");
+  R4R_REQUIRE(idx || (pad_id >= 0 && pad_id < V), R4R_EINVAL, "conv_pool_tc: pad id %lld outside the table", (long long)pad_id);
   R4R_REQUIRE(V > 0 && E > 0 && T > 0 && N >= 0, R4R_EINVAL, "conv_pool_tc: bad sizes");
   R4R_REQUIRE((T + 2 + 2 * TILE_M - 1) / (2 * TILE_M) <= 256, R4R_EUNSUP, "conv_pool_tc: T=%d exceeds 256 position tiles", T);
   R4R_REQUIRE(dtype == R4R_DT_F16 || dtype == R4R_DT_BF16, R4R_EINVAL, "conv_pool_tc: dtype %d", dtype);
@@ -709,6 +749,9 @@ extern "C" int r4r_conv_pool_tc(const void* shadow, int64_t V, int Epad, int E, 
   P.row_bytes = (long long)Epad * 2;
   P.V = V;
   P.idx = reinterpret_cast<const long long*>(idx);
+  P.tok32 = idx ? nullptr : tok32;
+  P.off = reinterpret_cast<const long long*>(off);
+  P.pad_id = pad_id;
   P.N = N; P.T = T; P.Kc = pl.Kc; P.F = F; P.Npad = pl.Npad;
   P.wpack = static_cast<const uint8_t*>(wpack);
   P.bias = conv_b; P.pooled = pooled; P.argmax = argmax;
@@ -723,4 +766,24 @@ extern "C" int r4r_conv_pool_tc(const void* shadow, int64_t V, int Epad, int E, 
   conv_pool_tc_kernel<<<(unsigned)(2 * nclusters), NUM_THREADS, smem_bytes, as_stream(stream)>>>(P);
   R4R_CHECK_LAUNCH("conv_pool_tc");
   return 0;
+}
+
+extern "C" int r4r_conv_pool_tc(const void* shadow, int64_t V, int Epad, int E, int dtype,
+                                const int64_t* idx, int64_t N, int T,
+                                const void* wpack, const float* conv_b, int F,
+                                float* pooled, int32_t* argmax,
+                                const int32_t* doc_len, const int32_t* doc_order, void* stream) {
+  R4R_REQUIRE(idx, R4R_EINVAL, "conv_pool_tc: null pointer");
+  return conv_pool_tc_launch(shadow, V, Epad, E, dtype, idx, nullptr, nullptr, 0, N, T, wpack, conv_b, F, pooled, argmax,
+                             doc_len, doc_order, stream);
+}
+
+extern "C" int r4r_conv_pool_tc_ragged(const void* shadow, int64_t V, int Epad, int E, int dtype,
+                                       const int32_t* tokens, const int64_t* offsets, int64_t pad_id, int64_t N, int T,
+                                       const void* wpack, const float* conv_b, int F,
+                                       float* pooled, int32_t* argmax,
+                                       const int32_t* doc_len, const int32_t* doc_order, void* stream) {
+  R4R_REQUIRE(tokens && offsets, R4R_EINVAL, "conv_pool_tc_ragged: null pointer");
+  return conv_pool_tc_launch(shadow, V, Epad, E, dtype, nullptr, tokens, offsets, pad_id, N, T, wpack, conv_b, F, pooled, argmax,
+                             doc_len, doc_order, stream);
 }

@@ -50,6 +50,19 @@ __global__ void __launch_bounds__(THREADS) doc_extent_kernel(const int64_t* __re
   }
 }
 
+// ragged documents: the trailing padding run starts where the stored tokens end
+__global__ void __launch_bounds__(THREADS) doc_extent_ragged_kernel(const int64_t* __restrict__ offsets, int64_t N, int T, int tile,
+                                                                    int32_t* __restrict__ doc_len, int32_t* __restrict__ hist) {
+  for (int64_t n = (int64_t)blockIdx.x * THREADS + threadIdx.x; n < N; n += (int64_t)gridDim.x * THREADS) {
+    const int64_t s = __ldg(offsets + n + 1) - __ldg(offsets + n);
+    if (s < 0 || s > T) __trap();
+    const int len = s + 3 < T ? (int)s + 3 : T;
+    doc_len[n] = len;
+    const int c = (len + 2 + tile - 1) / tile;
+    atomicAdd(hist + (c < NCLASS ? c : NCLASS - 1), 1);
+  }
+}
+
 // counting sort by tile count, descending; order within a class is arbitrary
 __global__ void __launch_bounds__(THREADS) doc_order_kernel(const int32_t* __restrict__ doc_len, int64_t N, int tile,
                                                             const int32_t* __restrict__ hist, int32_t* __restrict__ cursor,
@@ -87,6 +100,25 @@ extern "C" int r4r_doc_plan(const int64_t* idx, int64_t N, int T, int32_t* doc_l
   R4R_CHECK_LAUNCH("doc_extent");
   b = cdiv64(N, THREADS);
   if (b > 148) b = 148;
+  doc_order_kernel<<<(unsigned)b, THREADS, 0, s>>>(doc_len, N, tile, hist, cursor, doc_order);
+  R4R_CHECK_LAUNCH("doc_order");
+  return 0;
+}
+
+extern "C" int r4r_doc_plan_ragged(const int64_t* offsets, int64_t N, int T, int32_t* doc_len, int32_t* doc_order, void* ws,
+                                   void* stream) {
+  R4R_REQUIRE(offsets && doc_len && doc_order && ws, R4R_EINVAL, "doc_plan_ragged: null pointer");
+  R4R_REQUIRE(N >= 0 && N < (1LL << 31) && T > 0, R4R_EINVAL, "doc_plan_ragged: bad sizes");
+  if (N == 0) return 0;
+  cudaStream_t s = as_stream(stream);
+  const int tile = 256;
+  int32_t* hist = static_cast<int32_t*>(ws);
+  int32_t* cursor = hist + NCLASS;
+  R4R_CUDA(cudaMemsetAsync(ws, 0, (size_t)r4r_doc_plan_ws_bytes(), s));
+  int64_t b = cdiv64(N, THREADS);
+  if (b > 148) b = 148;
+  doc_extent_ragged_kernel<<<(unsigned)b, THREADS, 0, s>>>(offsets, N, T, tile, doc_len, hist);
+  R4R_CHECK_LAUNCH("doc_extent_ragged");
   doc_order_kernel<<<(unsigned)b, THREADS, 0, s>>>(doc_len, N, tile, hist, cursor, doc_order);
   R4R_CHECK_LAUNCH("doc_order");
   return 0;

@@ -153,13 +153,16 @@ extern "C" int r4r_rows_scatter_add(const float* gout, const int64_t* ids, int64
 // t < off[n+1] - off[n], else pad_id.
 __global__ void __launch_bounds__(256) docs_expand_kernel(const int32_t* __restrict__ tokens, const int64_t* __restrict__ offsets,
                                                           int64_t N, int T, int64_t pad_id, int64_t* __restrict__ out) {
-  const int64_t total = N * (int64_t)T;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t n = i / T;
-    const int t = (int)(i - n * T);
+  // one warp per document: 256-byte coalesced stores, no per-element index arithmetic
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); n < N; n += warps) {
     const int64_t lo = __ldg(offsets + n), hi = __ldg(offsets + n + 1);
     if (hi < lo || hi - lo > T) __trap();
-    out[i] = t < hi - lo ? (int64_t)__ldg(tokens + lo + t) : pad_id;
+    const int len = (int)(hi - lo);
+    const int32_t* src = tokens + lo;
+    int64_t* dst = out + n * (int64_t)T;
+    for (int t = lane; t < T; t += 32) dst[t] = t < len ? (int64_t)__ldg(src + t) : pad_id;
   }
 }
 
@@ -169,7 +172,7 @@ extern "C" int r4r_docs_expand(const int32_t* tokens, const int64_t* offsets, in
   R4R_REQUIRE(N >= 0 && T > 0, R4R_EINVAL, "docs_expand: bad sizes");
   if (N == 0) return 0;
   R4R_REQUIRE(tokens, R4R_EINVAL, "docs_expand: null token pointer");
-  int64_t blocks = cdiv64(N * (int64_t)T, 256 * 4);
+  int64_t blocks = cdiv64(N, 8);
   if (blocks > 148 * 16) blocks = 148 * 16;
   docs_expand_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(tokens, offsets, N, T, pad_id, out);
   R4R_CHECK_LAUNCH("docs_expand");

@@ -126,7 +126,8 @@ template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& 
 
 template <typename T, int NV>
 __global__ void __launch_bounds__(HTHREADS) conv_wgrad_half_kernel(
-    const uint8_t* __restrict__ shadow, int64_t V, int row_bytes, int E, const int64_t* __restrict__ idx, int64_t N, int Tn,
+    const uint8_t* __restrict__ shadow, int64_t V, int row_bytes, int E, const int64_t* __restrict__ idx,
+    const int32_t* __restrict__ tok32, const int64_t* __restrict__ off, int64_t pad_id, int64_t N, int Tn,
     const int32_t* __restrict__ argmax, const float* __restrict__ pooled, const float* __restrict__ gpooled,
     int F, float* __restrict__ dW, float* __restrict__ db) {
   const int f = blockIdx.x;
@@ -152,10 +153,14 @@ __global__ void __launch_bounds__(HTHREADS) conv_wgrad_half_kernel(
   for (int64_t nb = n0; nb < n1; nb += HBATCH) {
     float g[HBATCH];
     int a[HBATCH];
+    int64_t dbase[HBATCH];
+    int dlen[HBATCH];
 #pragma unroll
     for (int b = 0; b < HBATCH; ++b) {
       const int64_t n = nb + b;
       const bool in = n < n1;
+      dbase[b] = (in && tok32) ? __ldg(off + n) : 0;
+      dlen[b] = (in && tok32) ? (int)(__ldg(off + n + 1) - dbase[b]) : 0;
       const float p = in ? __ldg(pooled + n * F + f) : 0.0f;
       const float gg = in ? __ldg(gpooled + n * F + f) : 0.0f;
       a[b] = in ? __ldg(argmax + n * F + f) : 0;
@@ -170,7 +175,11 @@ __global__ void __launch_bounds__(HTHREADS) conv_wgrad_half_kernel(
       for (int b = 0; b < HBATCH; ++b) {
         const int pos = a[b] + vj[v] - 2;          // document row feeding window row j
         const bool live = g[b] != 0.0f && pos >= 0 && pos < Tn;
-        tok[b] = live ? __ldg(idx + (nb + b) * (int64_t)Tn + pos) : -1;
+        tok[b] = -1;
+        if (live) {
+          if (tok32) tok[b] = pos < dlen[b] ? (int64_t)__ldg(tok32 + dbase[b] + pos) : pad_id;   // ragged: rows past the stored tokens are padding
+          else tok[b] = __ldg(idx + (nb + b) * (int64_t)Tn + pos);
+        }
       }
       uint4 row[HBATCH];
 #pragma unroll
@@ -227,10 +236,11 @@ extern "C" int r4r_conv_wgrad_argmax(const float* table, int64_t V, int E, const
   return 0;
 }
 
-extern "C" int r4r_conv_wgrad_argmax_h(const void* shadow, int64_t V, int Epad, int E, int dtype, const int64_t* idx, int64_t N,
-                                       int T, const int32_t* argmax, const float* pooled, const float* gpooled, int F,
-                                       float* dW, float* db, void* stream) {
-  R4R_REQUIRE(shadow && idx && argmax && pooled && gpooled && dW && db, R4R_EINVAL, "conv_wgrad_h: null pointer");
+static int conv_wgrad_h_launch(const void* shadow, int64_t V, int Epad, int E, int dtype, const int64_t* idx,
+                               const int32_t* tok32, const int64_t* off, int64_t pad_id, int64_t N,
+                               int T, const int32_t* argmax, const float* pooled, const float* gpooled, int F,
+                               float* dW, float* db, void* stream) {
+  R4R_REQUIRE(shadow && (idx || (tok32 && off)) && argmax && pooled && gpooled && dW && db, R4R_EINVAL, "conv_wgrad_h: null pointer");
   R4R_REQUIRE(V > 0 && E > 0 && T > 0 && N >= 0 && F > 0, R4R_EINVAL, "conv_wgrad_h: bad sizes");
   R4R_REQUIRE(dtype == R4R_DT_F16 || dtype == R4R_DT_BF16, R4R_EINVAL, "conv_wgrad_h: dtype %d", dtype);
   R4R_REQUIRE(Epad % 8 == 0 && Epad >= ((E + 7) / 8) * 8 && reinterpret_cast<uintptr_t>(shadow) % 16 == 0, R4R_EINVAL,
@@ -248,7 +258,7 @@ extern "C" int r4r_conv_wgrad_argmax_h(const void* shadow, int64_t V, int Epad, 
   const uint8_t* sh = static_cast<const uint8_t*>(shadow);
   const int rb = Epad * 2;
 #define R4R_WG_LAUNCH(TYPE, NV) \
-  conv_wgrad_half_kernel<TYPE, NV><<<grid, HTHREADS, 0, s>>>(sh, V, rb, E, idx, N, T, argmax, pooled, gpooled, F, dW, db)
+  conv_wgrad_half_kernel<TYPE, NV><<<grid, HTHREADS, 0, s>>>(sh, V, rb, E, idx, tok32, off, pad_id, N, T, argmax, pooled, gpooled, F, dW, db)
   if (dtype == R4R_DT_F16) {
     if (nvec <= HTHREADS) R4R_WG_LAUNCH(__half, 1); else if (nvec <= 2 * HTHREADS) R4R_WG_LAUNCH(__half, 2); else R4R_WG_LAUNCH(__half, 3);
   } else {
@@ -257,4 +267,20 @@ extern "C" int r4r_conv_wgrad_argmax_h(const void* shadow, int64_t V, int Epad, 
 #undef R4R_WG_LAUNCH
   R4R_CHECK_LAUNCH("conv_wgrad_h");
   return 0;
+}
+
+extern "C" int r4r_conv_wgrad_argmax_h(const void* shadow, int64_t V, int Epad, int E, int dtype, const int64_t* idx, int64_t N,
+                                       int T, const int32_t* argmax, const float* pooled, const float* gpooled, int F,
+                                       float* dW, float* db, void* stream) {
+  R4R_REQUIRE(idx, R4R_EINVAL, "conv_wgrad_h: null pointer");
+  return conv_wgrad_h_launch(shadow, V, Epad, E, dtype, idx, nullptr, nullptr, 0, N, T, argmax, pooled, gpooled, F, dW, db, stream);
+}
+
+extern "C" int r4r_conv_wgrad_argmax_h_ragged(const void* shadow, int64_t V, int Epad, int E, int dtype, const int32_t* tokens,
+                                              const int64_t* offsets, int64_t pad_id, int64_t N, int T, const int32_t* argmax,
+                                              const float* pooled, const float* gpooled, int F, float* dW, float* db,
+                                              void* stream) {
+  R4R_REQUIRE(tokens && offsets && pad_id >= 0 && pad_id < V, R4R_EINVAL, "conv_wgrad_h_ragged: null pointer or pad id outside the table");
+  return conv_wgrad_h_launch(shadow, V, Epad, E, dtype, nullptr, tokens, offsets, pad_id, N, T, argmax, pooled, gpooled, F, dW, db,
+                             stream);
 }

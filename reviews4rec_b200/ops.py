@@ -28,17 +28,35 @@ def get_doc_plan() -> bool:
     return _doc_plan
 
 
+# How the fused conv / wgrad kernels treat ``RaggedIdx`` documents in the tensor-core modes:
+# False (default) = rebuild the padded int64 ids first (r4r_docs_expand, two ~10 us kernels that become part
+# of a captured step); True = read the ragged tokens directly (r4r_*_ragged entry points: exact same results,
+# no padded tensor at all, but the conv's token prefetch is currently ~8 % slower on that path).
+_ragged_native = os.environ.get("R4R_RAGGED_NATIVE", "0") == "1"
+
+
+def set_ragged_native(on: bool) -> None:
+    global _ragged_native
+    _ragged_native = bool(on)
+
+
 def doc_lengths(idx: "torch.Tensor") -> "torch.Tensor":
     """Informative prefix length of every document of ``idx`` [N,T] (r4r_doc_plan): rows after it repeat
     one token and cannot change the max-pooled features."""
-    _need_cuda(idx)
-    idx = _i64c(idx)
-    N, T = idx.shape
-    doc_len = torch.empty(N, device=idx.device, dtype=torch.int32)
-    order = torch.empty(N, device=idx.device, dtype=torch.int32)
-    ws = torch.empty(_lib.lib.r4r_doc_plan_ws_bytes(), device=idx.device, dtype=torch.uint8)
-    if N:
+    if isinstance(idx, RaggedIdx):
+        rg = idx.reshape(-1, idx.shape[-1])
+        N, T, dev = int(rg.shape[0]), int(rg.shape[1]), rg.device
+    else:
+        _need_cuda(idx)
+        idx, rg = _i64c(idx), None
+        (N, T), dev = idx.shape, idx.device
+    doc_len = torch.empty(N, device=dev, dtype=torch.int32)
+    order = torch.empty(N, device=dev, dtype=torch.int32)
+    ws = torch.empty(_lib.lib.r4r_doc_plan_ws_bytes(), device=dev, dtype=torch.uint8)
+    if N and rg is None:
         call("r4r_doc_plan", _p(idx), N, T, _p(doc_len), _p(order), _p(ws), _stream())
+    elif N:
+        call("r4r_doc_plan_ragged", _p(rg.offsets), N, T, _p(doc_len), _p(order), _p(ws), _stream())
     return doc_len
 
 
@@ -112,6 +130,8 @@ def _i64c(t: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------------ gather
 def word_gather(table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     """nn.Embedding forward on the frozen word table (DeepCoNN.py:53-54).  Bit-exact row copies."""
+    if isinstance(idx, RaggedIdx):
+        idx = idx.padded()
     _need_cuda(table, idx)
     table, idx = _f32c(table), _i64c(idx)
     out = torch.empty(*idx.shape, table.shape[1], device=table.device, dtype=torch.float32)
@@ -143,6 +163,59 @@ class ShadowTable:
         return self.tensor
 
 
+class RaggedIdx:
+    """Token ids of ``[N, T]`` (or ``[N, R, W]``) padded documents kept ragged on the device: row r is
+    ``tokens[offsets[r]:offsets[r+1]]`` followed by ``pad_id`` up to the last dim.  It stands in for the
+    reference's padded ``LongTensor`` (data_fast.py:102-108) in ``model(data)``: the fused conv / wgrad
+    kernels read it directly, everything else goes through ``padded()``."""
+
+    def __init__(self, tokens: torch.Tensor, offsets: torch.Tensor, shape, pad_id: int = 0):
+        if tokens.dtype != torch.int32 or offsets.dtype != torch.int64:
+            raise TypeError("RaggedIdx wants int32 tokens and int64 offsets")
+        self.tokens, self.offsets, self.pad_id = tokens, offsets, int(pad_id)
+        self.shape = torch.Size(shape)
+        rows = 1
+        for d in self.shape[:-1]:
+            rows *= int(d)
+        if offsets.numel() != rows + 1:
+            raise ValueError("offsets must have %d entries for shape %s" % (rows + 1, tuple(self.shape)))
+
+    device = property(lambda self: self.tokens.device)
+    is_cuda = property(lambda self: self.tokens.is_cuda)
+    dtype = torch.int64
+
+    def dim(self):
+        return len(self.shape)
+
+    def numel(self):
+        return int(self.shape.numel())
+
+    def contiguous(self):
+        return self
+
+    def reshape(self, *shape):
+        shape = list(shape[0]) if len(shape) == 1 and not isinstance(shape[0], int) else list(shape)
+        total = self.numel()
+        if -1 in shape:
+            known = 1
+            for d in shape:
+                known *= d if d != -1 else 1
+            shape[shape.index(-1)] = total // max(known, 1)
+        if int(torch.Size(shape).numel()) != total or shape[-1] != self.shape[-1]:
+            raise RuntimeError("RaggedIdx.reshape must keep the document length (last dim): %s -> %s" % (tuple(self.shape), tuple(shape)))
+        return RaggedIdx(self.tokens, self.offsets, shape, self.pad_id)
+
+    view = reshape
+
+    def padded(self) -> torch.Tensor:
+        """The int64 tensor the reference's reader would have produced (r4r_docs_expand, exact)."""
+        _need_cuda(self.tokens, self.offsets)
+        rows, T = self.offsets.numel() - 1, int(self.shape[-1])
+        out = torch.empty(tuple(self.shape), device=self.tokens.device, dtype=torch.int64)
+        call("r4r_docs_expand", _p(self.tokens), _p(self.offsets), rows, T, self.pad_id, _p(out), _stream())
+        return out
+
+
 class PrebuiltShadow:
     """Half-precision word rows that already are in the conv kernel's layout ([V+1, Epad], row V zero):
     the per-step row cache a sharded word table receives from the owners (sharded.py).  There is no
@@ -163,9 +236,21 @@ def conv_pool_forward(idx: torch.Tensor, table: torch.Tensor, conv_w: torch.Tens
                       mode: str, shadow: Optional[ShadowTable] = None, want_shadow: bool = False):
     """Fused gather -> conv(3xE, pad 2) -> relu -> global max-pool.  Returns (pooled [N,F], argmax [N,F])
     (+ the half-precision shadow rows it read, (tensor, Epad) or None, when ``want_shadow``)."""
+    ragged = None
+    if isinstance(idx, RaggedIdx):
+        idx = idx.reshape(-1, idx.shape[-1])
+        if mode == "exact" or not _ragged_native:
+            idx = idx.padded()                                   # the fp32 kernels (and the default policy) read padded ids
+        else:
+            ragged, idx = idx, idx.tokens
     _need_cuda(idx, table, conv_w, conv_b)
-    idx, conv_w, conv_b = _i64c(idx), _f32c(conv_w), _f32c(conv_b)
-    N, T = idx.shape
+    conv_w, conv_b = _f32c(conv_w), _f32c(conv_b)
+    if ragged is None:
+        idx = _i64c(idx)
+        N, T = idx.shape
+    else:
+        _need_cuda(ragged.offsets)
+        N, T = int(ragged.shape[0]), int(ragged.shape[1])
     if table is None:
         if not isinstance(shadow, PrebuiltShadow) or mode == "exact":
             raise RuntimeError("conv_pool needs the fp32 word table (or prebuilt half-precision rows in f16/bf16 mode)")
@@ -201,10 +286,17 @@ def conv_pool_forward(idx: torch.Tensor, table: torch.Tensor, conv_w: torch.Tens
             doc_len = torch.empty(N, device=dev, dtype=torch.int32)
             doc_order = torch.empty(N, device=dev, dtype=torch.int32)
             ws = torch.empty(_lib.lib.r4r_doc_plan_ws_bytes(), device=dev, dtype=torch.uint8)
-            call("r4r_doc_plan", _p(idx), N, T, _p(doc_len), _p(doc_order), _p(ws), _stream())
+            if ragged is None:
+                call("r4r_doc_plan", _p(idx), N, T, _p(doc_len), _p(doc_order), _p(ws), _stream())
+            else:
+                call("r4r_doc_plan_ragged", _p(ragged.offsets), N, T, _p(doc_len), _p(doc_order), _p(ws), _stream())
         with _ConvTimer():
-            call("r4r_conv_pool_tc", _p(sh), V, shadow.epad, E, dt, _p(idx), N, T, _p(wpack), _p(conv_b), F,
-                 _p(pooled), _p(argmax), _p(doc_len), _p(doc_order), _stream())
+            if ragged is None:
+                call("r4r_conv_pool_tc", _p(sh), V, shadow.epad, E, dt, _p(idx), N, T, _p(wpack), _p(conv_b), F,
+                     _p(pooled), _p(argmax), _p(doc_len), _p(doc_order), _stream())
+            else:
+                call("r4r_conv_pool_tc_ragged", _p(sh), V, shadow.epad, E, dt, _p(ragged.tokens), _p(ragged.offsets),
+                     ragged.pad_id, N, T, _p(wpack), _p(conv_b), F, _p(pooled), _p(argmax), _p(doc_len), _p(doc_order), _stream())
         used = (sh, shadow.epad, V)
     return (pooled, argmax, used) if want_shadow else (pooled, argmax)
 
@@ -215,8 +307,13 @@ class _ConvPool(torch.autograd.Function):
         if table is not None and table.requires_grad:
             raise RuntimeError("the word table is frozen in the reference (DeepCoNN.py:15 freeze=True); "
                                "a trainable word table is not part of this path")
+        if isinstance(idx, RaggedIdx):
+            idx = idx.reshape(-1, idx.shape[-1])
+            if mode == "exact" or not _ragged_native:
+                idx = idx.padded()
         pooled, argmax, used = conv_pool_forward(idx, table, conv_w, conv_b, mode, shadow, want_shadow=True)
-        ctx.save_for_backward(idx, table, argmax, pooled)
+        ctx.ragged = idx if isinstance(idx, RaggedIdx) else None
+        ctx.save_for_backward(None if ctx.ragged is not None else idx, table, argmax, pooled)
         ctx.wshape = tuple(conv_w.shape)
         ctx.mode, ctx.used = mode, used
         ctx.mark_non_differentiable(argmax)
@@ -226,18 +323,23 @@ class _ConvPool(torch.autograd.Function):
     def backward(ctx, gpooled, _gargmax):
         idx, table, argmax, pooled = ctx.saved_tensors
         F, _, _, E = ctx.wshape
-        N, T = idx.shape
-        dW = torch.zeros(ctx.wshape, device=idx.device, dtype=torch.float32)
-        db = torch.zeros(F, device=idx.device, dtype=torch.float32)
+        rg = ctx.ragged
+        N, T = (int(rg.shape[0]), int(rg.shape[1])) if rg is not None else idx.shape
+        dW = torch.zeros(ctx.wshape, device=pooled.device, dtype=torch.float32)
+        db = torch.zeros(F, device=pooled.device, dtype=torch.float32)
         if ctx.used is None:
             call("r4r_conv_wgrad_argmax", _p(table), table.shape[0], E, _p(idx), N, T, _p(argmax), _p(pooled),
                  _p(_f32c(gpooled)), F, _p(dW), _p(db), _stream())
         else:
             # f16 / bf16 modes: gradient of what the tensor-core forward computed, from the same shadow rows
             sh, epad, V = ctx.used
-            call("r4r_conv_wgrad_argmax_h", _p(sh), V, epad, E,
-                 _lib.R4R_DT_F16 if ctx.mode == "f16" else _lib.R4R_DT_BF16, _p(idx), N, T, _p(argmax), _p(pooled),
-                 _p(_f32c(gpooled)), F, _p(dW), _p(db), _stream())
+            dt = _lib.R4R_DT_F16 if ctx.mode == "f16" else _lib.R4R_DT_BF16
+            if rg is None:
+                call("r4r_conv_wgrad_argmax_h", _p(sh), V, epad, E, dt, _p(idx), N, T, _p(argmax), _p(pooled),
+                     _p(_f32c(gpooled)), F, _p(dW), _p(db), _stream())
+            else:
+                call("r4r_conv_wgrad_argmax_h_ragged", _p(sh), V, epad, E, dt, _p(rg.tokens), _p(rg.offsets), rg.pad_id, N, T,
+                     _p(argmax), _p(pooled), _p(_f32c(gpooled)), F, _p(dW), _p(db), _stream())
         return None, None, dW, db, None, None
 
 

@@ -87,13 +87,14 @@ class _Slot:
     def __init__(self, reader, device):
         bsz = reader.bsz
         self.tok, self.off, self.off_host, self.pad = {}, {}, {}, {}
-        self.used = False
+        self.used, self.n = False, 0
         for k, rd in reader.docs.items():
             rows = bsz * rd.rows_per_item
             self.tok[k] = torch.empty(max(1, rd.max_batch_tokens(bsz)), device=device, dtype=torch.int32)
             self.off[k] = torch.empty(rows + 1, device=device, dtype=torch.int64)
             self.off_host[k] = torch.empty(rows + 1, dtype=torch.int64).pin_memory()
-            self.pad[k] = torch.empty((bsz,) + rd.tail, device=device, dtype=torch.int64)
+            if not reader.native:
+                self.pad[k] = torch.empty((bsz,) + rd.tail, device=device, dtype=torch.int64)
         self.small = {k: torch.empty((bsz,) + tuple(v.shape[1:]), device=device, dtype=v.dtype) for k, v in reader.small.items()}
 
 
@@ -101,7 +102,8 @@ class RaggedReader:
     DOC_KEYS = ("a", "d", "e")                               # this review, user document, item document
     SMALL_KEYS = ("b", "c", "f", "g", "h")
 
-    def __init__(self, hyper_params: dict, arrays: Dict[str, Optional[np.ndarray]], device, slots: int = 2):
+    def __init__(self, hyper_params: dict, arrays: Dict[str, Optional[np.ndarray]], device, slots: int = 2,
+                 native: bool = False):
         """``arrays``: the datasets ``a..h`` of one split as numpy arrays (``None`` for slots the model
         does not read, as ``iter_simple`` does for MF: data.py:350-358)."""
         self.hyper_params = hyper_params
@@ -109,6 +111,9 @@ class RaggedReader:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("RaggedReader stages batches on a CUDA device (no CPU fallback)")
+        # native=False: documents are expanded to the reference's padded int64 tensors (any consumer);
+        # native=True: they are handed over as ops.RaggedIdx, which this package's models read directly
+        self.native = bool(native)
         self.total = int(len(arrays["h"]))
         self.docs = {k: RaggedDocs(arrays[k]) for k in self.DOC_KEYS if arrays.get(k) is not None}
         self.small = {}
@@ -127,9 +132,9 @@ class RaggedReader:
         return self.total // self.bsz + int(self.total % self.bsz > 0)
 
     def stage(self, batch: int, slot: int):
-        """Enqueue on the copy stream: H2D of batch ``batch``'s ragged tokens / offsets / ids / ratings and
-        the expansion into slot ``slot``'s padded tensors.  Returns (data, y, n_ratings); consumers must
-        ``wait_ready(slot)`` first and ``release(slot)`` after their last use."""
+        """Enqueue on the copy stream the H2D of batch ``batch``'s ragged tokens / offsets / ids / ratings into
+        slot ``slot``.  Returns (data, y, n_ratings); consumers must ``wait_ready(slot)`` first (it also
+        expands the documents in padded mode) and ``release(slot)`` after their last use."""
         lo = (batch % len(self)) * self.bsz
         hi = min(self.total, lo + self.bsz)
         n = hi - lo
@@ -145,20 +150,37 @@ class RaggedReader:
                 S.tok[k][: tok.numel()].copy_(tok, non_blocking=True)
                 S.off[k][: off.numel()].copy_(off, non_blocking=True)
                 nbytes += tok.numel() * 4 + off.numel() * 8
-                call("r4r_docs_expand", _vp(S.tok[k]), _vp(S.off[k]), n * rd.rows_per_item, rd.T, rd.pad_id, _vp(S.pad[k]),
-                     ctypes.c_void_p(self.copy_stream.cuda_stream))
             for k, v in self.small.items():
                 S.small[k][:n].copy_(v[lo:hi], non_blocking=True)
                 nbytes += (hi - lo) * v[0].numel() * v.element_size()
             self._ready[slot].record(self.copy_stream)
+        S.n = n
         self.h2d_bytes_last = nbytes
         get = lambda d, k: d[k][:n] if k in d else None
-        data = [get(S.pad, "a"), get(S.small, "b"), get(S.small, "c"), get(S.pad, "d"), get(S.pad, "e"),
-                get(S.small, "f"), get(S.small, "g")]
+
+        def doc(k):
+            if k not in self.docs:
+                return None
+            if not self.native:
+                return S.pad[k][:n]
+            from .ops import RaggedIdx
+            rd = self.docs[k]
+            return RaggedIdx(S.tok[k], S.off[k][: n * rd.rows_per_item + 1], (n,) + rd.tail, rd.pad_id)
+
+        data = [doc("a"), get(S.small, "b"), get(S.small, "c"), doc("d"), doc("e"), get(S.small, "f"), get(S.small, "g")]
         return data, S.small["h"][:n], n
 
     def wait_ready(self, slot: int, stream=None):
-        (stream or torch.cuda.current_stream()).wait_event(self._ready[slot])
+        """Make ``stream`` wait for the slot's copies and -- padded mode -- rebuild the padded int64 documents
+        on it (the expansion runs on the consumer's stream, right before the step, so it never competes
+        with the previous step's kernels for the SMs)."""
+        stream = stream or torch.cuda.current_stream()
+        stream.wait_event(self._ready[slot])
+        if not self.native:
+            S = self.slots[slot]
+            for k, rd in self.docs.items():
+                call("r4r_docs_expand", _vp(S.tok[k]), _vp(S.off[k]), S.n * rd.rows_per_item, rd.T, rd.pad_id, _vp(S.pad[k]),
+                     ctypes.c_void_p(stream.cuda_stream))
 
     def release(self, slot: int, stream=None):
         self._free[slot].record(stream or torch.cuda.current_stream())

@@ -227,7 +227,8 @@ class ShardedWordTable(nn.Module):
         from .pytorch_models.common_pytorch_models import Docs
         dev = self.weight.device
         flags, slot, req, rreq = self._scratch(dev)
-        idx_list = [i.contiguous() for i in idx_list]
+        # ragged documents are expanded first (the sharded lookup marks / remaps padded id tensors)
+        idx_list = [(i.padded() if isinstance(i, ops.RaggedIdx) else i).contiguous() for i in idx_list]
         for idx in idx_list:
             K.mark(idx, self.V, flags)
         K.plan(flags, self.V, self.P, self.cap, req, slot)

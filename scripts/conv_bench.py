@@ -15,6 +15,7 @@ ap.add_argument("--V", type=int, default=50001)
 ap.add_argument("--dist", default="amazon")
 ap.add_argument("--mode", default="f16")
 ap.add_argument("--iters", type=int, default=5)
+ap.add_argument("--ragged", action="store_true")
 a = ap.parse_args()
 rng = np.random.default_rng(0)
 pool = []
@@ -25,7 +26,12 @@ for i in range(3):
         idx = _Zipf(a.V - 1, 1.0).draw(rng, (a.docs, a.T))
     else:
         idx = rng.integers(0, a.V, (a.docs, a.T))
-    pool.append(torch.from_numpy(idx).cuda())
+    if a.ragged:
+        from reviews4rec_b200.readers import RaggedDocs
+        rd = RaggedDocs(idx, pin=False)
+        pool.append(ops.RaggedIdx(rd.tokens.cuda(), rd.offsets.cuda(), idx.shape, 0))
+    else:
+        pool.append(torch.from_numpy(idx).cuda())
 g = torch.Generator(device="cuda").manual_seed(0)
 table = (torch.rand(a.V, a.E, device="cuda", generator=g) - 0.5) * 0.07
 w = (torch.rand(100, 1, 3, a.E, device="cuda", generator=g) - 0.5) * 0.15
@@ -49,8 +55,8 @@ for i in range(a.iters):
 ms = sum(ts) / len(ts)
 print("whole call (pack + plan + conv): %.3f ms" % (sum(tot) / len(tot)))
 fl = 2.0 * (a.T + 2) * 100 * 3 * a.E * a.docs
-print("conv_bench dist=%s docs=%d mode=%s env=%s: %.3f ms/launch  %.1f TFLOP/s  %.0f docs/s  alg %.0f GB/s" % (
-    a.dist, a.docs, a.mode, {k: v for k, v in os.environ.items() if k.startswith("R4R_")}, ms, fl / ms / 1e9,
+print("conv_bench ragged=%s dist=%s docs=%d mode=%s env=%s: %.3f ms/launch  %.1f TFLOP/s  %.0f docs/s  alg %.0f GB/s" % (
+    a.ragged, a.dist, a.docs, a.mode, {k: v for k, v in os.environ.items() if k.startswith("R4R_")}, ms, fl / ms / 1e9,
     a.docs / ms * 1e3, a.docs * a.T * (8 + 4 * a.E) / ms / 1e6))
 if os.environ.get("CONV_PROF"):
     from reviews4rec_b200 import _lib

@@ -69,3 +69,96 @@ def test_ragged_reader_matches_padded_arrays(mt, N, B):
             assert y.dtype == torch.float32 and np.array_equal(y.cpu().numpy(), arrays["h"][seen:seen + n].astype(np.float32))
             seen += n
         assert seen == N
+
+
+def _ragged_on_device(arr):
+    from reviews4rec_b200.ops import RaggedIdx
+    from reviews4rec_b200.readers import RaggedDocs
+    rd = RaggedDocs(arr, pin=False)
+    return RaggedIdx(rd.tokens.cuda(), rd.offsets.cuda(), arr.shape, rd.pad_id)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["f16", "bf16", "exact"])
+@pytest.mark.parametrize("N,T,E,V", [(70, 1000, 300, 400), (33, 300, 64, 90), (24, 9, 12, 30)])
+def test_conv_and_wgrad_on_ragged_docs_match_padded(mode, N, T, E, V):
+    """The kernels reading ragged documents must give the bits they give on the expanded padded ids."""
+    from reviews4rec_b200 import ops
+    rng = np.random.default_rng(4)
+    arr = _padded(rng, (N,), V, T)
+    g = torch.Generator().manual_seed(2)
+    table = (torch.randn(V, E, generator=g) * 0.5).cuda()
+    w = (torch.randn(100, 1, 3, E, generator=g) * (1.0 / (3 * E) ** 0.5)).cuda()
+    b = (torch.randn(100, generator=g) * 0.1).cuda()
+    gout = torch.randn(N, 100, generator=g).cuda()
+    rg = _ragged_on_device(arr)
+    assert torch.equal(rg.padded().cpu(), torch.from_numpy(arr))
+    assert int(ops.doc_lengths(rg).max()) <= T
+    outs = []
+    try:
+        for idx, native in ((torch.from_numpy(arr).cuda(), False), (rg, True), (rg, False)):
+            ops.set_ragged_native(native)
+            wc, bc = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+            pooled, arg = ops._ConvPool.apply(idx, table, wc, bc, mode, None)
+            pooled.backward(gout)
+            outs.append((pooled.detach(), arg, wc.grad, bc.grad))
+    finally:
+        ops.set_ragged_native(False)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0][0], outs[2][0]) and torch.equal(outs[0][1], outs[2][1])
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    torch.testing.assert_close(outs[0][2], outs[1][2], rtol=1e-5, atol=1e-6)        # atomics: summation order only
+    torch.testing.assert_close(outs[0][3], outs[1][3], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mt", ["deepconn", "NARRE", "transnet++"])
+def test_models_read_native_ragged_batches(mt):
+    """RaggedReader(native=True) hands ops.RaggedIdx documents to the models: same ratings (bit-exact) and
+    the same short training run as with the expanded padded batches."""
+    import pickle, tempfile, os
+    import reviews4rec_b200 as R
+    from reviews4rec_b200 import ops
+    from reviews4rec_b200.optim import FusedAdam
+    from reviews4rec_b200.readers import RaggedReader
+    from reviews4rec_b200.train import train
+    from reviews4rec_b200.utils import init_transnet_optim, xavier_init
+    rng = np.random.default_rng(7)
+    N, B, T, Rv, W, V, E, L, U, I = 24, 8, 300, 4, 40, 120, 32, 6, 30, 20
+    tmp = tempfile.mkdtemp()
+    with open(os.path.join(tmp, "word2vec.pkl"), "wb") as f:
+        pickle.dump(np.zeros((V, E), dtype=np.float32), f, 4)
+    hp = {"model_type": mt, "latent_size": L, "word_embed_size": E, "dropout": 0.0, "total_users": U, "total_items": I,
+          "lr": 0.002, "weight_decay": 1e-6, "batch_size": B, "data_dir": tmp}
+    arrays = {k: None for k in "abcdefgh"}
+    arrays["f"], arrays["g"] = rng.integers(0, U, N), rng.integers(0, I, N)
+    arrays["h"] = rng.integers(1, 6, N).astype(np.float64)
+    if mt == "NARRE":
+        arrays["d"], arrays["e"] = _padded(rng, (N, Rv), V, W), _padded(rng, (N, Rv), V, W)
+        arrays["b"], arrays["c"] = rng.integers(0, U + 2, (N, Rv)), rng.integers(0, I + 2, (N, Rv))   # one neighbour id per review
+    else:
+        arrays["d"], arrays["e"] = _padded(rng, (N,), V, T), _padded(rng, (N,), V, T)
+        arrays["a"] = _padded(rng, (N,), V, T)
+    ops.set_conv_mode("f16")
+    results = []
+    for native in (False, True):
+        ops.set_ragged_native(native)
+        torch.manual_seed(0)
+        cls = {"deepconn": R.DeepCoNN, "NARRE": R.NARRE, "transnet++": R.TransNet}[mt]
+        model = cls(hp)
+        xavier_init(model)
+        model = model.cuda()
+        reader = RaggedReader(hp, arrays, "cuda", native=native)
+        model.eval()
+        with torch.no_grad():
+            first = next(iter(reader.iter()))
+            out = model(first[0])
+            out = [o.clone() for o in out] if isinstance(out, list) else [out.clone()]
+        torch.cuda.synchronize()
+        opt = init_transnet_optim(hp, model, FusedAdam) if mt.startswith("transnet") else FusedAdam(model.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"])
+        train(model, R.MSELoss(hp), opt, reader, hp)
+        results.append((out, train.last_raw["se_sum"]))
+    ops.set_ragged_native(False)
+    for a, b in zip(results[0][0], results[1][0]):
+        assert torch.equal(a, b)
+    assert abs(results[0][1] - results[1][1]) <= 1e-5 * abs(results[0][1])
