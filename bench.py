@@ -36,8 +36,10 @@ HP = {"model_type": "deepconn", "latent_size": 10, "word_embed_size": 300, "inpu
       "total_users": 1000000, "total_items": 100000, "lr": 0.002, "weight_decay": 1e-6, "batch_size": 4096,
       "narre_num_reviews": 10, "narre_num_words": 200}
 METRIC = "train ratings/sec DeepCoNN synthetic Amazon-shape"
-# dram__bytes_read.sum + dram__bytes_write.sum of one conv_pool_tc launch at B=4096 (ncu --set full, profiles/)
-NCU_CONV_DRAM_BYTES_PER_LAUNCH = 67.2e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one conv_pool_tc launch at B=4096 (ncu --set full,
+# profiles/r1_v19_conv_ncu_raw.csv) and of one whole step (ncu launch list profiles/r1_v19_launches_bench.csv / 21 steps)
+NCU_CONV_DRAM_BYTES_PER_LAUNCH = 45.8e6
+NCU_STEP_DRAM_BYTES = 206.5e6
 REF_SAMPLE_B = 128            # ratings per reference-arm step (the reference's own default batch, hyper_params.py:60)
 
 
@@ -190,7 +192,7 @@ def run_b200(args):
     group = None
     if world > 1:
         import faulthandler
-        faulthandler.dump_traceback_later(max(300, args.steps), exit=True)   # a hung collective must not run forever
+        faulthandler.dump_traceback_later(900, exit=True)   # a hung collective must not run forever
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
@@ -459,7 +461,11 @@ def run_b200(args):
                              "algorithmic_* = the reference's dense work (all T+2 positions, fp32 rows + int64 ids) / the same time"},
         "step_roofline": {"bytes_per_rating": algorithmic_bytes_per_rating(hp),
                           "achieved_gbs": algorithmic_bytes_per_rating(hp) * value / world / 1e9,
-                          "frac_of_hbm_peak": algorithmic_bytes_per_rating(hp) * value / world / 1e9 / hbm_peak},
+                          "frac_of_hbm_peak": algorithmic_bytes_per_rating(hp) * value / world / 1e9 / hbm_peak,
+                          "traffic_per_step": NCU_STEP_DRAM_BYTES if (B == 4096 and world == 1) else None,
+                          "note": "algorithmic bytes as the reference stores them (fp32 rows + int64 ids, SURVEY.md 8d); the step "
+                                  "actually moves traffic_per_step bytes of DRAM (frozen table in half precision, L2-resident), "
+                                  "which is why the fraction can exceed 1"},
         "train_mse": train_mse,
         "clocks": clocks,
     }
