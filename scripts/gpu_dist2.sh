@@ -3,10 +3,7 @@
 mkdir -p gpurun_out
 (timeout 420 python -m pytest tests/test_gpu_sharded.py -q --tb=short 2>&1 | tail -30) | tee gpurun_out/t_sharded2.log
 for tr in nccl p2p; do
-  (timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 2951$((RANDOM%10)) \
-     bench.py --gpus 2 --steps 200 --warmup 10 --transport $tr 2> gpurun_out/bench2_$tr.err) | tee gpurun_out/bench2_$tr.json | cut -c1-250
+  (timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 2951$((RANDOM%10)) \
+     bench.py --gpus 2 --transport $tr 2> gpurun_out/bench2_$tr.err) | tee gpurun_out/bench2_$tr.json | cut -c1-250
   tail -n 4 gpurun_out/bench2_$tr.err | cut -c1-300
 done
-(timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29525 \
-   bench.py --gpus 2 --steps 200 --warmup 10 --table replicated 2> gpurun_out/bench2_repl.err) | tee gpurun_out/bench2_repl.json | cut -c1-250
-tail -n 4 gpurun_out/bench2_repl.err | cut -c1-300
