@@ -194,6 +194,7 @@ def run_b200(args):
         import faulthandler
         faulthandler.dump_traceback_later(900, exit=True)   # a hung collective must not run forever
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries exactly one JSON line (NCCL logs its version there otherwise)
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
 
