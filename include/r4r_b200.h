@@ -52,6 +52,23 @@ int r4r_word_gather_f32(const float* table, int64_t V, int E, const int64_t* idx
 int r4r_docs_expand(const int32_t* tokens, const int64_t* offsets, int64_t N, int T, int64_t pad_id, int64_t* out,
                     void* stream);
 
+/* On-device document assembly.  The train reviews live once in device memory as CSR:
+ * tok (all reviews back to back), rev_off [n_reviews+1], and per side (user or item) the review lists
+ * ptr [n_lists+1] / rev (review ids in list order) / nb (the item -- resp. user -- behind every list entry).
+ * For rating b of list ids[b], leaving out list entry skip[b] (-1 / NULL: none), this builds what the
+ * reference's slow reader builds in Python (data.py:212-248 remove_overlap, :174-210 pad_and_join,
+ * :146-172 pad_only, :277-282 neighbour padding):
+ *   mode 0: out_docs[b, 0:T]      = kept reviews concatenated, cut to T, zero padded
+ *   mode 1: out_docs[b, r, 0:W]   = kept review r cut / zero padded to W, r < R, missing reviews all zero
+ *   out_nb[b, 0:nbw]              = nb of the kept reviews, padded with nb_pad, cut to nbw          (optional)
+ *   out_this[b, ...]              = the left-out review as a document of the same shape, or -- this_tok
+ *                                   given -- row this_row0 + b of the held-out review CSR           (optional) */
+int r4r_docs_assemble(const int32_t* tok, const int64_t* rev_off, const int64_t* ptr, const int32_t* rev,
+                      const int64_t* nb, int64_t n_lists, const int64_t* ids, const int32_t* skip, int64_t B,
+                      int mode, int T, int R, int W, int64_t nb_pad, int nbw,
+                      int64_t* out_docs, int64_t* out_nb, int64_t* out_this,
+                      const int32_t* this_tok, const int64_t* this_off, int64_t this_row0, void* stream);
+
 /* Private reduced-precision copy of the frozen word table (SURVEY.md finding 2):
  * shadow[v, 0:E] = cvt(table[v,:]), shadow[v, E:Epad] = 0.  Epad % 8 == 0, row stride = Epad.
  * `shadow` holds V+1 rows: row V is all zero (r4r_conv_pool_tc reads the conv's zero padding from it). */

@@ -25,6 +25,8 @@ SIGNATURES = {
     "r4r_device_info": (c_int, [ctypes.POINTER(c_int)] * 3 + [ctypes.POINTER(c_i64)]),
     "r4r_word_gather_f32": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_vp]),
     "r4r_docs_expand": (c_int, [c_vp, c_vp, c_i64, c_int, c_i64, c_vp, c_vp]),
+    "r4r_docs_assemble": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_i64, c_int,
+                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "r4r_shadow_build": (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_int, c_vp]),
     "r4r_conv_pool_simt": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
     "r4r_conv_wpack_bytes": (c_i64, [c_int, c_int]),

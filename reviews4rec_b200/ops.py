@@ -100,6 +100,42 @@ class _ConvTimer:
             _conv_event_sink.append((self.e0, self.e1))
 
 
+# ------------------------------------------------------------------------------------ zero arena
+# The parameter-gradient kernels accumulate with atomics, so every backward needs zeroed dW / db / dV buffers:
+# ~14 tiny fill kernels per DeepCoNN step.  Inside a captured step they are carved out of ONE flat buffer that
+# a single memset clears at the start of the step (train.CapturedStep calls arena_begin / arena_end).
+class _ZeroArena:
+    buf: Optional[torch.Tensor] = None
+    ofs = 0
+    active = False
+    FLOATS = 1 << 20
+
+
+def arena_begin(device, floats: int = _ZeroArena.FLOATS) -> None:
+    a = _ZeroArena
+    if a.buf is None or a.buf.device != torch.device(device) or a.buf.numel() < floats:
+        a.buf = torch.empty(floats, device=device, dtype=torch.float32)
+    a.buf.zero_()
+    a.ofs, a.active = 0, True
+
+
+def arena_end() -> None:
+    _ZeroArena.active = False
+
+
+def zeros_f32(shape, device) -> torch.Tensor:
+    """Zero-filled fp32 tensor: a 16-byte aligned slice of the step's arena when one is active."""
+    a = _ZeroArena
+    n = 1
+    for d in shape:
+        n *= int(d)
+    if a.active and a.buf.device == torch.device(device) and a.ofs + n <= a.buf.numel():
+        out = a.buf[a.ofs:a.ofs + n].view(tuple(shape))
+        a.ofs += (n + 3) & ~3
+        return out
+    return torch.zeros(tuple(shape), device=device, dtype=torch.float32)
+
+
 def _p(t: Optional[torch.Tensor]):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
@@ -325,8 +361,8 @@ class _ConvPool(torch.autograd.Function):
         F, _, _, E = ctx.wshape
         rg = ctx.ragged
         N, T = (int(rg.shape[0]), int(rg.shape[1])) if rg is not None else idx.shape
-        dW = torch.zeros(ctx.wshape, device=pooled.device, dtype=torch.float32)
-        db = torch.zeros(F, device=pooled.device, dtype=torch.float32)
+        dW = zeros_f32(ctx.wshape, pooled.device)
+        db = zeros_f32((F,), pooled.device)
         if ctx.used is None:
             call("r4r_conv_wgrad_argmax", _p(table), table.shape[0], E, _p(idx), N, T, _p(argmax), _p(pooled),
                  _p(_f32c(gpooled)), F, _p(dW), _p(db), _stream())
@@ -370,8 +406,8 @@ class _Linear(torch.autograd.Function):
         n, in_f = x.shape
         out_f = W.shape[0]
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        dW = torch.zeros_like(W) if ctx.needs_input_grad[1] else None
-        db = torch.zeros(out_f, device=x.device, dtype=torch.float32) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        dW = zeros_f32(W.shape, x.device) if ctx.needs_input_grad[1] else None
+        db = zeros_f32((out_f,), x.device) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         call("r4r_linear_bwd", _p(x), _p(W), _p(gy), n, in_f, out_f, _p(dx), _p(dW), _p(db), _stream())
         return dx, dW, db
 
@@ -402,9 +438,9 @@ class _FM(torch.autograd.Function):
         n, nf = x.shape
         k = V.shape[1]
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        dV = torch.zeros_like(V)
-        dw = torch.zeros_like(lin_w)
-        db = torch.zeros(1, device=x.device, dtype=torch.float32)
+        dV = zeros_f32(V.shape, x.device)
+        dw = zeros_f32(lin_w.shape, x.device)
+        db = zeros_f32((1,), x.device)
         call("r4r_fm_bwd", _p(x), _p(V), _p(lin_w), _p(_f32c(gout)), n, nf, k, _p(dx), _p(dV), _p(dw), _p(db), _stream())
         return dx, dV, dw, db
 

@@ -198,3 +198,117 @@ class RaggedReader:
             self.wait_ready(slot)
             yield cur[0], cur[1]
             self.release(slot)
+
+
+# ------------------------------------------------------------------------------------------ review-level CSR
+def review_list_side(ids, other, n_lists):
+    """Review lists of one side (host, numpy).  ``ids[n]`` = the list (user or item) train review n belongs to,
+    ``other[n]`` = the id on the opposite side.  Returns ``ptr`` [n_lists+1], ``rev`` (review ids in list order =
+    train order within a list, as preprocess_random_split.py:213-218 appends them), ``nb`` (``other`` in list
+    order: u_to_i_map / i_to_u_map) and ``rank[n]`` = position of review n inside its list
+    (this_index_user_item[user][item][0 or 1])."""
+    ids, other = np.asarray(ids, dtype=np.int64), np.asarray(other, dtype=np.int64)
+    n = ids.shape[0]
+    if n and (ids.min() < 0 or ids.max() >= n_lists):
+        raise ValueError("review_list_side: id outside [0, %d)" % n_lists)
+    order = np.argsort(ids, kind="stable")
+    ptr = np.concatenate([[0], np.cumsum(np.bincount(ids, minlength=n_lists))]).astype(np.int64)
+    rank = np.empty(n, dtype=np.int32)
+    rank[order] = (np.arange(n) - ptr[ids[order]]).astype(np.int32)
+    return ptr, order.astype(np.int32), other[order], rank
+
+
+class ReviewStore:
+    """The train reviews of a dataset, resident ONCE in device memory.
+
+    Built from the train split in rating order -- review n is the text of train rating n, exactly how
+    preprocess_random_split.py:207-219 fills ``user_reviews`` / ``item_reviews`` / ``this_index_user_item`` --
+    as CSR: ``tok`` (int32, all reviews back to back), ``rev_off``, and per side the review lists
+    ``ptr`` / ``rev`` / ``nb`` (``nb`` = ``u_to_i_map`` / ``i_to_u_map`` of data.py:36-63).  ``rank_user[n]`` /
+    ``rank_item[n]`` are ``this_index_user_item[user][item]``: where review n sits in its user's / item's list.
+    """
+
+    def __init__(self, tok, rev_off, train_user, train_item, total_users: int, total_items: int, device):
+        tok = np.ascontiguousarray(np.asarray(tok, dtype=np.int32))
+        rev_off = np.ascontiguousarray(np.asarray(rev_off, dtype=np.int64))
+        tu = np.asarray(train_user, dtype=np.int64)
+        ti = np.asarray(train_item, dtype=np.int64)
+        n = tu.shape[0]
+        if rev_off.shape[0] != n + 1 or ti.shape[0] != n or int(rev_off[-1]) != tok.shape[0]:
+            raise ValueError("ReviewStore: one review per train rating (rev_off must have n + 1 entries ending at len(tok))")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("ReviewStore lives in device memory (no CPU fallback)")
+        self.U, self.I, self.n = int(total_users), int(total_items), n
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+
+        self.tok, self.rev_off = dev(tok), dev(rev_off)
+        (ptr, rev, nb, rank_u), (iptr, irev, inb, rank_i) = review_list_side(tu, ti, self.U), review_list_side(ti, tu, self.I)
+        self.u_ptr, self.u_rev, self.u_nb = dev(ptr), dev(rev), dev(nb)
+        self.i_ptr, self.i_rev, self.i_nb = dev(iptr), dev(irev), dev(inb)
+        self.train_user, self.train_item = dev(tu), dev(ti)
+        self.rank_user, self.rank_item = dev(rank_u), dev(rank_i)
+        self.bytes = sum(t.numel() * t.element_size() for t in (self.tok, self.rev_off, self.u_ptr, self.u_rev, self.u_nb,
+                                                                self.i_ptr, self.i_rev, self.i_nb))
+
+
+class CsrReader:
+    """Reader protocol of ``main.train`` / ``eval.evaluate`` over a ``ReviewStore``: every batch's seven
+    inputs are assembled on the device (``r4r_docs_assemble``); nothing but the batch bounds comes from the
+    host.  ``train=True`` iterates the store's own train ratings (each rating's own review is left out of both
+    documents and becomes ``this_reviews``); otherwise ``users`` / ``items`` / ``ratings`` are an evaluation split
+    and ``this_tok`` / ``this_off`` its held-out reviews as CSR (``test_reviews`` of data.py:239-241)."""
+
+    NBW = 10                                                            # data.py:277-282
+
+    def __init__(self, hyper_params: dict, store: ReviewStore, ratings, train: bool, users=None, items=None,
+                 this_tok=None, this_off=None):
+        self.hp, self.store, self.train = hyper_params, store, bool(train)
+        self.bsz = int(hyper_params["batch_size"])
+        dev = store.device
+        to = lambda a, dt: torch.from_numpy(np.ascontiguousarray(np.asarray(a))).to(dt).to(dev)
+        if train:
+            self.users, self.items = store.train_user, store.train_item
+        else:
+            self.users, self.items = to(users, torch.int64), to(items, torch.int64)
+        self.y = to(ratings, torch.float32)
+        self.total = int(self.y.shape[0])
+        if self.users.shape[0] != self.total:
+            raise ValueError("CsrReader: one rating per (user, item)")
+        self.this_tok = to(this_tok, torch.int32) if this_tok is not None else None
+        self.this_off = to(this_off, torch.int64) if this_off is not None else None
+        self.narre = hyper_params["model_type"] == "NARRE"
+        self.simple = hyper_params["model_type"] in ("bias_only", "MF", "MF_dot", "NeuMF")      # data.py:33-34 iter_simple
+        self.T = int(hyper_params.get("input_length", 1000))
+        self.R, self.W = int(hyper_params.get("narre_num_reviews", 10)), int(hyper_params.get("narre_num_words", 200))
+
+    def __len__(self):
+        return self.total // self.bsz + int(self.total % self.bsz > 0)
+
+    def batch(self, lo: int, hi: int):
+        st, n, dev = self.store, hi - lo, self.store.device
+        users, items, y = self.users[lo:hi], self.items[lo:hi], self.y[lo:hi]
+        if self.simple:
+            return [None, None, None, None, None, users, items], y
+        shape = (n, self.R, self.W) if self.narre else (n, self.T)
+        udoc = torch.empty(shape, device=dev, dtype=torch.int64)
+        idoc = torch.empty(shape, device=dev, dtype=torch.int64)
+        this = torch.empty(shape, device=dev, dtype=torch.int64)
+        items_reviewed = torch.empty(n, self.NBW, device=dev, dtype=torch.int64)
+        users_who_gave = torch.empty(n, self.NBW, device=dev, dtype=torch.int64)
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        mode = 1 if self.narre else 0
+        sk_u = st.rank_user[lo:hi] if self.train else None
+        sk_i = st.rank_item[lo:hi] if self.train else None
+        eval_this = (not self.train) and self.this_tok is not None
+        call("r4r_docs_assemble", _vp(st.tok), _vp(st.rev_off), _vp(st.u_ptr), _vp(st.u_rev), _vp(st.u_nb), st.U, _vp(users), _vp(sk_u), n,
+             mode, self.T, self.R, self.W, st.I + 1, self.NBW, _vp(udoc), _vp(items_reviewed), _vp(this),
+             _vp(self.this_tok if eval_this else None), _vp(self.this_off if eval_this else None), lo, stream)
+        call("r4r_docs_assemble", _vp(st.tok), _vp(st.rev_off), _vp(st.i_ptr), _vp(st.i_rev), _vp(st.i_nb), st.I, _vp(items), _vp(sk_i), n,
+             mode, self.T, self.R, self.W, st.U + 1, self.NBW, _vp(idoc), _vp(users_who_gave), _vp(None),
+             _vp(None), _vp(None), 0, stream)
+        return [this, users_who_gave, items_reviewed, udoc, idoc, users, items], y
+
+    def iter(self, eval=False):
+        for lo in range(0, self.total, self.bsz):
+            yield self.batch(lo, min(self.total, lo + self.bsz))

@@ -101,7 +101,9 @@ class CapturedStep:
         model.zero_grad(set_to_none=True)
         self.graph = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
+        from . import ops
         with torch.cuda.graph(self.graph):
+            ops.arena_begin(dev)                    # one memset for all the zeroed gradient buffers of the step
             out = model(data)
             se = criterion(out, y, return_mean=False)
             self.se_sum += se.detach().sum()
@@ -112,6 +114,7 @@ class CapturedStep:
                 from .sharded import allreduce_dense_grads
                 allreduce_dense_grads(model, group, int(grad_div))
             optimizer.step()
+            ops.arena_end()
         self.out = out
 
     def replay(self):

@@ -1,0 +1,110 @@
+"""The document-assembly oracle (oracle/r4r_data_oracle.py) against what the unmodified reference reader
+yielded for the seeded dataset of oracle/gen_golden_docs.py (tests/golden/docs_*.npz)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.helpers import GOLDEN
+
+
+def load_docs_golden(mt):
+    z = np.load(os.path.join(GOLDEN, "docs_%s.npz" % mt))
+    U, I, V, T, R, W, B = [int(x) for x in z["dims"]]
+    hp = {"model_type": mt, "batch_size": B, "input_length": T, "narre_num_reviews": R, "narre_num_words": W,
+          "total_users": U, "total_items": I}
+    return z, hp, (U, I, V)
+
+
+def split_reviews(tok, off):
+    return [tok[off[k]:off[k + 1]].tolist() for k in range(len(off) - 1)]
+
+
+@pytest.mark.parametrize("mt", ["deepconn", "NARRE"])
+def test_oracle_reproduces_reference_reader(mt):
+    from oracle import r4r_data_oracle as D
+    z, hp, (U, I, V) = load_docs_golden(mt)
+    lists = D.review_lists(z["train_user"], z["train_item"], split_reviews(z["tok"], z["rev_off"]), U, I)
+    for split, train in (("train", True), ("eval", False)):
+        test_reviews = None if train else split_reviews(z["eval_tok"], z["eval_off"])
+        got = list(D.batches(z[split + "_user"], z[split + "_item"], z[split + "_y"], lists, hp, train, test_reviews))
+        assert len(got) == int(z[split + ".nb"][0])
+        for b, (data, y) in enumerate(got):
+            for j, d in enumerate(data):
+                want = z["%s.b%d.d%d" % (split, b, j)]
+                assert np.array_equal(np.array(d, dtype=np.int64), want), (split, b, j)
+            assert np.array_equal(np.array(y, dtype=np.float32), z["%s.b%d.y" % (split, b)])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mt", ["deepconn", "NARRE"])
+def test_device_assembly_reproduces_reference_reader(mt):
+    """ReviewStore + CsrReader (r4r_docs_assemble) yield, bit for bit, the batches the unmodified reference
+    reader produced (golden), for the train split (own review left out) and an evaluation split."""
+    import torch
+    from reviews4rec_b200.readers import CsrReader, ReviewStore
+    z, hp, (U, I, V) = load_docs_golden(mt)
+    store = ReviewStore(z["tok"], z["rev_off"], z["train_user"], z["train_item"], U, I, "cuda")
+    readers = {"train": CsrReader(hp, store, z["train_y"], train=True),
+               "eval": CsrReader(hp, store, z["eval_y"], train=False, users=z["eval_user"], items=z["eval_item"],
+                                 this_tok=z["eval_tok"], this_off=z["eval_off"])}
+    for split, reader in readers.items():
+        assert len(reader) == int(z[split + ".nb"][0])
+        for b, (data, y) in enumerate(reader.iter()):
+            for j, d in enumerate(data):
+                want = z["%s.b%d.d%d" % (split, b, j)]
+                assert d.dtype == torch.int64 and np.array_equal(d.cpu().numpy(), want), (split, b, j)
+            assert np.array_equal(y.cpu().numpy(), z["%s.b%d.y" % (split, b)])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mt,T", [("deepconn", 1000), ("NARRE", 0), ("transnet", 257)])
+def test_device_assembly_vs_oracle_larger(mt, T):
+    """Random larger dataset (heavy users whose documents overflow input_length, empty reviews, users without
+    reviews): device assembly == the pinned oracle."""
+    import torch
+    from oracle import r4r_data_oracle as D
+    from reviews4rec_b200.readers import CsrReader, ReviewStore
+    rng = np.random.default_rng(3)
+    U, I, V, n, B = 40, 25, 500, 600, 64
+    pairs = set()
+    while len(pairs) < n + 50:
+        u = int(rng.integers(0, U - 2)) if rng.random() < 0.7 else 0
+        pairs.add((u, int(rng.integers(0, I - 1))))
+    pairs = rng.permutation(sorted(pairs))
+    lens = rng.integers(0, 120, len(pairs))
+    revs = [rng.integers(1, V, k).astype(np.int32) for k in lens]
+    tr, ev = slice(0, n), slice(n, len(pairs))
+    tok = np.concatenate(revs[tr]); off = np.concatenate([[0], np.cumsum(lens[tr])])
+    etok = np.concatenate(revs[ev]); eoff = np.concatenate([[0], np.cumsum(lens[ev])])
+    y = rng.integers(1, 6, len(pairs)).astype(np.float32)
+    hp = {"model_type": mt, "batch_size": B, "input_length": T or 1000, "narre_num_reviews": 10, "narre_num_words": 50,
+          "total_users": U, "total_items": I}
+    store = ReviewStore(tok, off, pairs[tr, 0], pairs[tr, 1], U, I, "cuda")
+    lists = D.review_lists(pairs[tr, 0], pairs[tr, 1], [r.tolist() for r in revs[tr]], U, I)
+    cases = [(CsrReader(hp, store, y[tr], train=True), D.batches(pairs[tr, 0], pairs[tr, 1], y[tr], lists, hp, True)),
+             (CsrReader(hp, store, y[ev], train=False, users=pairs[ev, 0], items=pairs[ev, 1], this_tok=etok, this_off=eoff),
+              D.batches(pairs[ev, 0], pairs[ev, 1], y[ev], lists, hp, False, [r.tolist() for r in revs[ev]]))]
+    for reader, want in cases:
+        for (data, yy), (wd, wy) in zip(reader.iter(), want):
+            for j in range(7):
+                assert np.array_equal(data[j].cpu().numpy(), np.array(wd[j], dtype=np.int64)), j
+            assert np.array_equal(yy.cpu().numpy(), np.array(wy, dtype=np.float32))
+
+
+def test_review_list_side_matches_this_index_user_item():
+    """Host logic of ReviewStore (CPU): list order, neighbour ids and ranks equal the reference's
+    user_reviews / u_to_i_map / this_index_user_item construction."""
+    from oracle import r4r_data_oracle as D
+    from reviews4rec_b200.readers import review_list_side
+    z, hp, (U, I, V) = load_docs_golden("deepconn")
+    tu, ti = z["train_user"], z["train_item"]
+    revs = split_reviews(z["tok"], z["rev_off"])
+    user_reviews, item_reviews, this_index, u_to_i, i_to_u = D.review_lists(tu, ti, revs, U, I)
+    for ids, other, n_lists, lists, nbmap, col in ((tu, ti, U, user_reviews, u_to_i, 0), (ti, tu, I, item_reviews, i_to_u, 1)):
+        ptr, rev, nb, rank = review_list_side(ids, other, n_lists)
+        for l in range(n_lists):
+            got = [revs[r] for r in rev[ptr[l]:ptr[l + 1]]]
+            assert got == lists[l] and nb[ptr[l]:ptr[l + 1]].tolist() == nbmap[l]
+        for n in range(len(tu)):
+            assert int(rank[n]) == this_index[int(tu[n])][int(ti[n])][col]

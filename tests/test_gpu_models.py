@@ -191,3 +191,33 @@ def test_oracle_agrees_at_larger_shapes(mt):
             assert_close(p.grad, grads[n], rtol=2e-4, atol=2e-6, msg="grad " + n)
         else:
             assert p.grad is None, n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mt", ["deepconn", "deepconn++", "NARRE"])
+def test_captured_step_equals_eager_training(mt):
+    """train.CapturedStep (CUDA graph, zero arena, capturable FusedAdam) replays the same training as the
+    eager loop: identical parameters after three passes over the golden batches."""
+    import reviews4rec_b200 as R
+    from reviews4rec_b200.optim import FusedAdam
+    from reviews4rec_b200.train import CapturedStep, train
+    z, dims = load_golden(mt)
+    batches = golden_batches(z, dims, "cuda")
+    eager, hp = build(mt, z, dims, mode="f16")
+    opt = FusedAdam(eager.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"])
+    for _ in range(3):
+        train(eager, R.MSELoss(hp), opt, ListReader(batches), hp)
+    graph_model, _ = build(mt, z, dims, mode="f16")
+    graph_model.train()
+    gopt = FusedAdam(graph_model.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"], capturable=True)
+    se = torch.zeros(1, device="cuda")
+    steps = [CapturedStep(graph_model, R.MSELoss(hp), gopt, d, y, se) for d, y in batches]
+    for _ in range(3):
+        for s in steps:
+            s.replay()
+    torch.cuda.synchronize()
+    a, b = eager.state_dict(), graph_model.state_dict()
+    for k in a:
+        # same tolerances as the reference train-loop test: atomics make the gradient summation order vary
+        atol = hp["lr"] * 3 * dims["NB"] if (mt == "NARRE" and k.startswith("attention_scorer_") and k.endswith(".3.bias")) else 4e-6
+        assert_close(b[k], a[k], rtol=1e-4, atol=atol, msg="%s %s" % (mt, k))
