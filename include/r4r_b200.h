@@ -163,6 +163,9 @@ int r4r_mse_fwd(const float* out, const float* y, int64_t n, float* se, float* s
 /* gout[n] = gse[n] * 2*(out[n]-y[n])   (gse = upstream grad of se, e.g. 1/B for the mean) */
 int r4r_mse_bwd(const float* out, const float* y, const float* gse, int64_t n, float* gout, void* stream);
 
+/* idx[r] = index of the first largest x[r, 0:c]: the top-1 candidate of eval.eval_ranking (eval.py:74-78) */
+int r4r_rows_argmax(const float* x, int64_t n, int c, int64_t* idx, void* stream);
+
 /* ---- a7-a10: id-embedding / bias row gathers and their gradient scatter ----------------------
  * out[i,:] = table[ids[i],:]   replaces nn.Embedding / Tensor.gather at MF.py:45-46,52-53,
  * NARRE.py:87-88,110-116, TransNet.py:108-109, DeepCoNN.py:70-71  (L = 1 for the bias vectors) */

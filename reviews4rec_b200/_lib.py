@@ -46,6 +46,7 @@ SIGNATURES = {
     "r4r_fm_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "r4r_mse_fwd": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "r4r_mse_bwd": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "r4r_rows_argmax": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
     "r4r_rows_gather": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_vp]),
     "r4r_rows_scatter_add": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_vp]),
     "r4r_adam_step": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp] + [c_f32] * 5 + [c_vp]),

@@ -212,6 +212,20 @@ __global__ void __launch_bounds__(THREADS) mse_bwd_kernel(const float* __restric
     gout[i] = gse[i] * 2.0f * (out[i] - y[i]);
 }
 
+// index of the (first) largest score per row: the top-1 pick of eval.py:74-78 (torch.topk(output[b], k=1))
+__global__ void __launch_bounds__(THREADS) rows_argmax_kernel(const float* __restrict__ x, int64_t n, int c, int64_t* __restrict__ idx) {
+  for (int64_t r = (int64_t)blockIdx.x * THREADS + threadIdx.x; r < n; r += (int64_t)gridDim.x * THREADS) {
+    const float* row = x + r * (int64_t)c;
+    float best = row[0];
+    int at = 0;
+    for (int j = 1; j < c; ++j) {
+      const float v = row[j];
+      if (v > best) { best = v; at = j; }
+    }
+    idx[r] = at;
+  }
+}
+
 inline unsigned grid_for(int64_t work_items, int per_block, int cap = 148 * 8) {
   int64_t b = cdiv64(work_items, per_block);
   if (b < 1) b = 1;
@@ -284,5 +298,14 @@ extern "C" int r4r_mse_bwd(const float* out, const float* y, const float* gse, i
   if (n <= 0) return 0;
   mse_bwd_kernel<<<grid_for(n, THREADS, 148), THREADS, 0, as_stream(stream)>>>(out, y, gse, n, gout);
   R4R_CHECK_LAUNCH("mse_bwd");
+  return 0;
+}
+
+extern "C" int r4r_rows_argmax(const float* x, int64_t n, int c, int64_t* idx, void* stream) {
+  R4R_REQUIRE(x && idx, R4R_EINVAL, "rows_argmax: null pointer");
+  R4R_REQUIRE(n >= 0 && c > 0, R4R_EINVAL, "rows_argmax: bad sizes");
+  if (n == 0) return 0;
+  rows_argmax_kernel<<<grid_for(n, THREADS, 148 * 4), THREADS, 0, as_stream(stream)>>>(x, n, c, idx);
+  R4R_CHECK_LAUNCH("rows_argmax");
   return 0;
 }
