@@ -32,13 +32,17 @@ __global__ void __launch_bounds__(THREADS) doc_extent_kernel(const int64_t* __re
     const int64_t* row = idx + n * (int64_t)T;
     const int64_t last = __ldg(row + T - 1);
     int s = 0;                                        // start of the trailing run
-    for (int hi = T; hi > 0; hi -= 32) {              // window [hi-32, hi)
-      const int t = hi - 32 + lane;
-      const bool same = t < 0 || __ldg(row + t) == last;
-      const unsigned diff = ~__ballot_sync(0xffffffffu, same);
-      if (diff) {
-        s = hi - 32 + (32 - __clz(diff));             // one past the highest differing position
-        break;
+    for (int hi = T; hi > 0 && s == 0; hi -= 128) {   // four 32-token windows [hi-32(w+1), hi-32w) per trip, loads issued together
+      int64_t v[4];
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const int t = hi - 32 * (w + 1) + lane;
+        v[w] = t >= 0 ? __ldg(row + t) : last;
+      }
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const unsigned diff = ~__ballot_sync(0xffffffffu, v[w] == last);
+        if (diff && s == 0) s = hi - 32 * (w + 1) + (32 - __clz(diff));   // one past the highest differing position
       }
     }
     if (lane == 0) {

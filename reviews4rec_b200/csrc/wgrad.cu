@@ -124,7 +124,19 @@ template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& 
   for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); x[2 * i] = f.x; x[2 * i + 1] = f.y; }
 }
 
-template <typename T, int NV>
+// Per batch of HBATCH documents the loads form a dependent chain  (pooled, grad, argmax) -> token id -> row.
+// The loop is software-pipelined three deep: while the rows of batch k are fetched and accumulated, the token
+// ids of batch k+1 and the (pooled, grad, argmax) triples of batch k+2 are already in flight, so a thread
+// exposes one memory latency per batch instead of three.
+template <bool RAGGED>
+struct WgMeta {
+  float g[HBATCH];
+  int a[HBATCH];
+  int64_t base[RAGGED ? HBATCH : 1];
+  int len[RAGGED ? HBATCH : 1];
+};
+
+template <typename T, int NV, bool RAGGED>
 __global__ void __launch_bounds__(HTHREADS) conv_wgrad_half_kernel(
     const uint8_t* __restrict__ shadow, int64_t V, int row_bytes, int E, const int64_t* __restrict__ idx,
     const int32_t* __restrict__ tok32, const int64_t* __restrict__ off, int64_t pad_id, int64_t N, int Tn,
@@ -150,51 +162,76 @@ __global__ void __launch_bounds__(HTHREADS) conv_wgrad_half_kernel(
   }
   float bsum = 0.0f;
 
-  for (int64_t nb = n0; nb < n1; nb += HBATCH) {
-    float g[HBATCH];
-    int a[HBATCH];
-    int64_t dbase[HBATCH];
-    int dlen[HBATCH];
+  // stage A: (pooled, grad, argmax) [+ document extent] of the documents nb .. nb+HBATCH-1
+  auto stage_a = [&](int64_t nb, WgMeta<RAGGED>& m) {
 #pragma unroll
     for (int b = 0; b < HBATCH; ++b) {
       const int64_t n = nb + b;
       const bool in = n < n1;
-      dbase[b] = (in && tok32) ? __ldg(off + n) : 0;
-      dlen[b] = (in && tok32) ? (int)(__ldg(off + n + 1) - dbase[b]) : 0;
+      if (RAGGED) {
+        m.base[b] = in ? __ldg(off + n) : 0;
+        m.len[b] = in ? (int)(__ldg(off + n + 1) - m.base[b]) : 0;
+      }
       const float p = in ? __ldg(pooled + n * F + f) : 0.0f;
       const float gg = in ? __ldg(gpooled + n * F + f) : 0.0f;
-      a[b] = in ? __ldg(argmax + n * F + f) : 0;
-      g[b] = p > 0.0f ? gg : 0.0f;                 // dead ReLU -> no gradient (CTA-uniform)
-      bsum += g[b];
+      m.a[b] = in ? __ldg(argmax + n * F + f) : 0;
+      m.g[b] = p > 0.0f ? gg : 0.0f;               // dead ReLU -> no gradient (CTA-uniform)
     }
+  };
+  // stage B: token id of the document row feeding this thread's window row j (-1 = nothing to add)
+  auto stage_b = [&](int64_t nb, const WgMeta<RAGGED>& m, int64_t (&tok)[NV][HBATCH]) {
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
-      if (vj[v] < 0) continue;
-      int64_t tok[HBATCH];
 #pragma unroll
       for (int b = 0; b < HBATCH; ++b) {
-        const int pos = a[b] + vj[v] - 2;          // document row feeding window row j
-        const bool live = g[b] != 0.0f && pos >= 0 && pos < Tn;
-        tok[b] = -1;
+        const int pos = m.a[b] + vj[v] - 2;
+        const bool live = vj[v] >= 0 && m.g[b] != 0.0f && pos >= 0 && pos < Tn;
+        int64_t t = -1;
         if (live) {
-          if (tok32) tok[b] = pos < dlen[b] ? (int64_t)__ldg(tok32 + dbase[b] + pos) : pad_id;   // ragged: rows past the stored tokens are padding
-          else tok[b] = __ldg(idx + (nb + b) * (int64_t)Tn + pos);
+          if (RAGGED) t = pos < m.len[b] ? (int64_t)__ldg(tok32 + m.base[b] + pos) : pad_id;   // rows past the stored tokens are padding
+          else t = __ldg(idx + (nb + b) * (int64_t)Tn + pos);
         }
+        tok[v][b] = t;
       }
+    }
+  };
+  // stage C: gather the rows and accumulate
+  auto stage_c = [&](const WgMeta<RAGGED>& m, const int64_t (&tok)[NV][HBATCH]) {
+#pragma unroll
+    for (int b = 0; b < HBATCH; ++b) bsum += m.g[b];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
       uint4 row[HBATCH];
 #pragma unroll
       for (int b = 0; b < HBATCH; ++b) {
         row[b] = make_uint4(0u, 0u, 0u, 0u);
-        if (tok[b] >= 0) row[b] = __ldg(reinterpret_cast<const uint4*>(shadow + tok[b] * (int64_t)row_bytes) + vc[v]);
+        if (tok[v][b] >= 0) row[b] = __ldg(reinterpret_cast<const uint4*>(shadow + tok[v][b] * (int64_t)row_bytes) + vc[v]);
       }
 #pragma unroll
       for (int b = 0; b < HBATCH; ++b) {
         float x[8];
         unpack8<T>(row[b], x);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[v][i] = fmaf(g[b], x[i], acc[v][i]);
+        for (int i = 0; i < 8; ++i) acc[v][i] = fmaf(m.g[b], x[i], acc[v][i]);
       }
     }
+  };
+
+  WgMeta<RAGGED> m_c, m_b, m_a;                   // metadata of the batches in stages C, B, A
+  int64_t t_c[NV][HBATCH], t_b[NV][HBATCH];
+  stage_a(n0, m_c);
+  stage_a(n0 + HBATCH, m_b);
+  stage_b(n0, m_c, t_c);
+  for (int64_t nb = n0; nb < n1; nb += HBATCH) {
+    stage_a(nb + 2 * HBATCH, m_a);                // k+2
+    stage_b(nb + HBATCH, m_b, t_b);               // k+1
+    stage_c(m_c, t_c);                            // k
+    m_c = m_b;
+    m_b = m_a;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int b = 0; b < HBATCH; ++b) t_c[v][b] = t_b[v][b];
   }
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
@@ -258,7 +295,10 @@ static int conv_wgrad_h_launch(const void* shadow, int64_t V, int Epad, int E, i
   const uint8_t* sh = static_cast<const uint8_t*>(shadow);
   const int rb = Epad * 2;
 #define R4R_WG_LAUNCH(TYPE, NV) \
-  conv_wgrad_half_kernel<TYPE, NV><<<grid, HTHREADS, 0, s>>>(sh, V, rb, E, idx, tok32, off, pad_id, N, T, argmax, pooled, gpooled, F, dW, db)
+  do {                                                                                                                         \
+    if (tok32) conv_wgrad_half_kernel<TYPE, NV, true><<<grid, HTHREADS, 0, s>>>(sh, V, rb, E, idx, tok32, off, pad_id, N, T, argmax, pooled, gpooled, F, dW, db); \
+    else conv_wgrad_half_kernel<TYPE, NV, false><<<grid, HTHREADS, 0, s>>>(sh, V, rb, E, idx, tok32, off, pad_id, N, T, argmax, pooled, gpooled, F, dW, db);      \
+  } while (0)
   if (dtype == R4R_DT_F16) {
     if (nvec <= HTHREADS) R4R_WG_LAUNCH(__half, 1); else if (nvec <= 2 * HTHREADS) R4R_WG_LAUNCH(__half, 2); else R4R_WG_LAUNCH(__half, 3);
   } else {
