@@ -141,6 +141,15 @@ int r4r_conv_wgrad_argmax_h(const void* shadow, int64_t V, int Epad, int E, int 
                             int T, const int32_t* argmax, const float* pooled, const float* gpooled, int F,
                             float* dW, float* db, void* stream);
 
+/* OPT-IN (not reference behaviour: the reference freezes the word table, DeepCoNN.py:15): gradient of the
+ * conv w.r.t. the word table through relu + max-pool,
+ *   gtable[idx[n, argmax[n,f] + j - 2], :] += gy[n,f] * conv_w[f,0,j,:]     (positions outside [0,T) skipped)
+ * accumulated into the dense [V,E] gradient; per document, updates of the same row are summed first
+ * (sorted segments) so that each (row, column) receives one atomic. */
+int r4r_conv_dgrad_scatter(const int64_t* idx, int64_t N, int T, const int32_t* argmax, const float* pooled,
+                           const float* gpooled, const float* conv_w, int F, int E, float* gtable, int64_t V,
+                           void* stream);
+
 /* ---- small dense layers of the heads ----------------------------------------------------------
  * y[n,o] = sum_i x[n,i] W[o,i] + b[o]   (nn.Linear: TextCNN.fc common_pytorch_models.py:19,37;
  * DeepCoNN.final DeepCoNN.py:21-26; NARRE scorers NARRE.py:24-43; TransNet project TransNet.py:17-21) */

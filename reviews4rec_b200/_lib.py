@@ -40,6 +40,7 @@ SIGNATURES = {
     "r4r_conv_debug_profile": (c_int, [c_vp]),
     "r4r_conv_wgrad_argmax": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
     "r4r_conv_wgrad_argmax_h": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
+    "r4r_conv_dgrad_scatter": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_i64, c_vp]),
     "r4r_linear_fwd": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp]),
     "r4r_linear_bwd": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     "r4r_fm_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp]),

@@ -1,0 +1,105 @@
+// dgrad.cu -- OPT-IN: gradient of the TextCNN conv w.r.t. the word-embedding table.
+//
+// Not reference behaviour: the reference freezes the table (nn.Embedding.from_pretrained default
+// freeze=True, DeepCoNN.py:15; SURVEY.md finding 2), so there is no parity claim against it -- the checker
+// is autograd on the oracle with the table marked trainable.  Through ReLU + global max-pool only the
+// arg-max window of each (document, filter) carries gradient, so
+//     dTable[idx[n, a(n,f) + j - 2], :] += gy[n,f] * W[f, 0, j, :]        j = 0..2,  gy = gpooled * [pooled > 0]
+// i.e. <= 3F row updates per document instead of a dense [N, T, E] gradient.
+// One CTA per document: the (position, filter*3+j, gy) entries are sorted by position in shared memory and
+// every run of equal positions is summed in registers before ONE atomicAdd per (row, column) -- the padding
+// window that many filters pick, and neighbouring windows that overlap, collapse into single updates.
+#include "common.cuh"
+
+namespace {
+constexpr int THREADS = 128;
+constexpr int MAX_ENT = 512;           // >= 3 * F entries per document (F <= 128), power of two for the bitonic sort
+constexpr int MAXC = 8;                // columns per thread: E <= MAXC * THREADS = 1024
+
+__global__ void __launch_bounds__(THREADS) conv_dgrad_scatter_kernel(
+    const int64_t* __restrict__ idx, int64_t N, int T, const int32_t* __restrict__ argmax, const float* __restrict__ pooled,
+    const float* __restrict__ gpooled, const float* __restrict__ conv_w, int F, int E, float* __restrict__ gtable, int64_t V) {
+  __shared__ uint32_t key[MAX_ENT];    // pos << 9 | (f*3 + j); 0xffffffff = empty
+  __shared__ float val[MAX_ENT];
+  const int tid = threadIdx.x;
+  for (int64_t n = blockIdx.x; n < N; n += gridDim.x) {
+    for (int q = tid; q < MAX_ENT; q += THREADS) {
+      uint32_t k = 0xffffffffu;
+      float g = 0.0f;
+      if (q < 3 * F) {
+        const int f = q / 3, j = q - 3 * f;
+        const float p = __ldg(pooled + n * F + f);
+        const float gg = __ldg(gpooled + n * F + f);
+        const int pos = __ldg(argmax + n * F + f) + j - 2;
+        if (p > 0.0f && gg != 0.0f && pos >= 0 && pos < T) { k = ((uint32_t)pos << 9) | (uint32_t)q; g = gg; }
+      }
+      key[q] = k;
+      val[q] = g;
+    }
+    __syncthreads();
+    // bitonic sort of (key, val) ascending; empty entries sink to the end
+    for (int size = 2; size <= MAX_ENT; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int q = tid; q < MAX_ENT / 2; q += THREADS) {
+          const int i = 2 * q - (q & (stride - 1));
+          const int p2 = i + stride;
+          const bool up = (i & size) == 0;
+          const uint32_t ka = key[i], kb = key[p2];
+          if ((ka > kb) == up) {
+            key[i] = kb; key[p2] = ka;
+            const float t = val[i]; val[i] = val[p2]; val[p2] = t;
+          }
+        }
+        __syncthreads();
+      }
+    }
+    // segmented accumulate: every thread owns columns tid, tid + THREADS, ...
+    float acc[MAXC];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) acc[c] = 0.0f;
+    int cur = -1;
+    for (int q = 0; q <= 3 * F && q <= MAX_ENT; ++q) {
+      const uint32_t k = (q < 3 * F && q < MAX_ENT) ? key[q] : 0xffffffffu;
+      const int pos = k == 0xffffffffu ? -1 : (int)(k >> 9);
+      if (pos != cur) {
+        if (cur >= 0) {
+          const int64_t tok = __ldg(idx + n * (int64_t)T + cur);
+          if (tok < 0 || tok >= V) __trap();
+          float* dst = gtable + tok * (int64_t)E;
+#pragma unroll
+          for (int c = 0; c < MAXC; ++c) {
+            const int e = tid + c * THREADS;
+            if (e < E && acc[c] != 0.0f) atomicAdd(dst + e, acc[c]);
+            acc[c] = 0.0f;
+          }
+        }
+        cur = pos;
+        if (pos < 0) break;                       // sorted: only empty entries follow
+      }
+      const float g = val[q];
+      const float* wrow = conv_w + (int64_t)(k & 511u) * E;     // W[f, 0, j, :] is row f*3 + j of the [F*3, E] view
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        const int e = tid + c * THREADS;
+        if (e < E) acc[c] = fmaf(g, __ldg(wrow + e), acc[c]);
+      }
+    }
+    __syncthreads();
+  }
+}
+}  // namespace
+
+extern "C" int r4r_conv_dgrad_scatter(const int64_t* idx, int64_t N, int T, const int32_t* argmax, const float* pooled,
+                                      const float* gpooled, const float* conv_w, int F, int E, float* gtable, int64_t V,
+                                      void* stream) {
+  R4R_REQUIRE(idx && argmax && pooled && gpooled && conv_w && gtable, R4R_EINVAL, "conv_dgrad_scatter: null pointer");
+  R4R_REQUIRE(N >= 0 && T > 0 && F > 0 && E > 0 && V > 0, R4R_EINVAL, "conv_dgrad_scatter: bad sizes");
+  R4R_REQUIRE(3 * F <= MAX_ENT && E <= MAXC * THREADS && T + 2 < (1 << 22), R4R_EUNSUP,
+              "conv_dgrad_scatter: F=%d (<= %d) E=%d (<= %d)", F, MAX_ENT / 3, E, MAXC * THREADS);
+  if (N == 0) return 0;
+  int64_t blocks = N < 148 * 8 ? N : 148 * 8;
+  conv_dgrad_scatter_kernel<<<(unsigned)blocks, THREADS, 0, as_stream(stream)>>>(idx, N, T, argmax, pooled, gpooled, conv_w, F, E,
+                                                                                 gtable, V);
+  R4R_CHECK_LAUNCH("conv_dgrad_scatter");
+  return 0;
+}

@@ -188,7 +188,7 @@ class ShadowTable:
 
     def get(self, table: torch.Tensor, mode: str) -> torch.Tensor:
         key = (table.data_ptr(), table._version, tuple(table.shape), mode)
-        if key != self._key:
+        if key != self._key or table.requires_grad:     # a trainable table (opt-in) changes under the optimizer's raw kernels
             V, E = table.shape
             self.epad = ((E + 63) // 64) * 64                     # 128-byte aligned rows
             dt = torch.float16 if mode == "f16" else torch.bfloat16
@@ -340,9 +340,10 @@ def conv_pool_forward(idx: torch.Tensor, table: torch.Tensor, conv_w: torch.Tens
 class _ConvPool(torch.autograd.Function):
     @staticmethod
     def forward(ctx, idx, table, conv_w, conv_b, mode, shadow):
-        if table is not None and table.requires_grad:
-            raise RuntimeError("the word table is frozen in the reference (DeepCoNN.py:15 freeze=True); "
-                               "a trainable word table is not part of this path")
+        # the reference freezes the word table (DeepCoNN.py:15): table.requires_grad is the opt-in extension of
+        # SURVEY.md 8f-3 (hyper_params['train_word_table']), served by r4r_conv_dgrad_scatter in backward
+        ctx.table_grad = table is not None and table.requires_grad
+        ctx.conv_w = conv_w.detach() if ctx.table_grad else None
         if isinstance(idx, RaggedIdx):
             idx = idx.reshape(-1, idx.shape[-1])
             if mode == "exact" or not _ragged_native:
@@ -376,7 +377,13 @@ class _ConvPool(torch.autograd.Function):
             else:
                 call("r4r_conv_wgrad_argmax_h_ragged", _p(sh), V, epad, E, dt, _p(rg.tokens), _p(rg.offsets), rg.pad_id, N, T,
                      _p(argmax), _p(pooled), _p(_f32c(gpooled)), F, _p(dW), _p(db), _stream())
-        return None, None, dW, db, None, None
+        gtable = None
+        if ctx.table_grad:
+            pidx = rg.padded() if rg is not None else idx
+            gtable = torch.zeros_like(table)
+            call("r4r_conv_dgrad_scatter", _p(pidx), N, T, _p(argmax), _p(pooled), _p(_f32c(gpooled)), _p(_f32c(ctx.conv_w)), F, E,
+                 _p(gtable), table.shape[0], _stream())
+        return None, gtable, dW, db, None, None
 
 
 def conv_pool(idx, table, conv_w, conv_b, mode=None, shadow=None):

@@ -13,7 +13,8 @@ class DeepCoNN(nn.Module):
         super().__init__()
         self.hyper_params = hyper_params
         L = hyper_params["latent_size"]
-        self.word2vec = WordTable.from_vectors(load_obj(hyper_params["data_dir"] + "/word2vec"))
+        self.word2vec = WordTable.from_vectors(load_obj(hyper_params["data_dir"] + "/word2vec"),
+                                                trainable=bool(hyper_params.get("train_word_table", False)))
         self.user_conv = TextCNN(hyper_params)
         self.item_conv = TextCNN(hyper_params)
         self.final = nn.Sequential(SmallLinear(2 * L, L), nn.ReLU(), nn.Dropout(hyper_params["dropout"]), SmallLinear(L, 1))

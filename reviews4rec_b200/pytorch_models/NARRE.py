@@ -14,7 +14,8 @@ class NARRE(nn.Module):
         super().__init__()
         self.hyper_params = hyper_params
         L, p = hyper_params["latent_size"], hyper_params["dropout"]
-        self.word2vec = WordTable.from_vectors(load_obj(hyper_params["data_dir"] + "/word2vec"))
+        self.word2vec = WordTable.from_vectors(load_obj(hyper_params["data_dir"] + "/word2vec"),
+                                                trainable=bool(hyper_params.get("train_word_table", False)))
         self.user_embedding = IdEmbedding(hyper_params["total_users"] + 2, L)
         self.item_embedding = IdEmbedding(hyper_params["total_items"] + 2, L)
         self.user_conv = TextCNN(hyper_params)

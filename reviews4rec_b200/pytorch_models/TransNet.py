@@ -29,7 +29,8 @@ class Target(nn.Module):
     def __init__(self, hyper_params):
         super().__init__()
         self.hyper_params = hyper_params
-        self.word2vec = WordTable.from_vectors(load_obj(hyper_params["data_dir"] + "/word2vec"))
+        self.word2vec = WordTable.from_vectors(load_obj(hyper_params["data_dir"] + "/word2vec"),
+                                                trainable=bool(hyper_params.get("train_word_table", False)))
         self.conv = TextCNN(hyper_params)
         self.dropout = nn.Dropout(hyper_params["dropout"])
         self.fm = TorchFM(hyper_params["latent_size"], 8)

@@ -24,9 +24,11 @@ class WordTable(nn.Embedding):
     Calling it returns a lazy ``Docs`` handle; the gather is fused into the conv kernel."""
 
     @classmethod
-    def from_vectors(cls, word_vectors):
+    def from_vectors(cls, word_vectors, trainable=False):
+        """``trainable=True`` (hyper_params['train_word_table']) is an opt-in extension, not reference
+        behaviour: the reference's table is frozen (SURVEY.md finding 2 / 8f-3)."""
         w = torch.as_tensor(word_vectors, dtype=torch.float32)
-        m = cls(w.shape[0], w.shape[1], _weight=w, _freeze=True)
+        m = cls(w.shape[0], w.shape[1], _weight=w, _freeze=not trainable)
         m.requires_grad = False          # same inert attribute the reference sets (DeepCoNN.py:16)
         m._shadow = ops.ShadowTable()
         return m
@@ -62,7 +64,8 @@ class TextCNN(nn.Module):
         if isinstance(x, Docs):
             return ops.conv_pool(x.idx, x.table, conv.weight, conv.bias, shadow=x.shadow)
         if x.requires_grad:
-            raise RuntimeError("TextCNN input gradients are not part of this path (the word table is frozen)")
+            raise RuntimeError("gradients w.r.t. a dense [N,T,E] TextCNN input are not part of this path; "
+                               "a trainable word table goes through the WordTable / Docs handle")
         n, t, e = x.shape                                   # reference signature: embedded docs [N,T,E]
         idx = torch.arange(n * t, device=x.device, dtype=torch.int64).view(n, t)
         return ops.conv_pool(idx, x.reshape(n * t, e), conv.weight, conv.bias, shadow=self._dense_shadow)

@@ -338,6 +338,9 @@ def shard_model(model: nn.Module, transport: Transport, shard_word_table: bool =
     P, rank = transport.world, transport.rank
     if shard_word_table:
         for mod, name, child in list(_word_table_owners(model)):
+            if child.weight.requires_grad:
+                raise RuntimeError("the sharded word lookup is forward-only (frozen table, as in the reference); "
+                                   "train_word_table needs the replicated table")
             setattr(mod, name, ShardedWordTable(child.weight.data, word_transport or transport).to(child.weight.device))
     params = dict(model.named_parameters())
     for key in SHARDED_PARAMS:
