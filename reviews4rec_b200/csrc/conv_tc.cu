@@ -49,8 +49,10 @@ constexpr int TILE_M = 128;            // positions per CTA per accumulator tile
 constexpr int RA = 131;                // rows per A slot: 130 needed (128 + 2 halo); odd => the
                                        // chunk stride RA*16 B maps 8 lanes onto 8 distinct bank groups
 constexpr int N_MAX = 128;             // filters (UMMA N), multiple of 16
-constexpr int ACC_STRIDE = 128;        // TMEM columns between the two accumulator buffers
-constexpr int TMEM_COLS = 256;
+constexpr int ACC_STRIDE = 128;        // TMEM columns between consecutive accumulator buffers
+constexpr int NACC = 4;                // accumulator buffers: the MMA warp may run three tiles ahead of the epilogue,
+                                       // which hides the per-document reduction (the epilogue drains nothing meanwhile)
+constexpr int TMEM_COLS = NACC * ACC_STRIDE;   // 512 = all of TMEM (1 CTA per SM)
 constexpr int NUM_EPI_WARPS = 8, NUM_PROD_WARPS = 4;
 constexpr int MMA_WARP = NUM_EPI_WARPS + NUM_PROD_WARPS;
 constexpr int NUM_THREADS = (MMA_WARP + 1) * 32;
@@ -58,13 +60,14 @@ constexpr int MAX_SLOTS = 8;
 constexpr int ROWS_PER_THREAD = 9;     // producer thread i copies rows i/8 + 16k, k < 9
 constexpr int CPS = 8;                 // 16-byte K-chunks per ring slab: one chunk column per producer lane (K = 64 per slab)
 constexpr int MAX_SPT = 16;            // slabs per position tile -> Kc <= 128 chunks (E <= 1024)
-constexpr int LAG = 2;                 // a slab is published after the next LAG ones have been issued
+constexpr int LAG = 2;                 // default: a slab is published after the next LAG ones have been issued
+constexpr int MAX_LAG = 4;             // tuning range (R4R_CONV_LAG); the ring needs lag + 2 slots
 
 struct SharedCtl {
   unsigned long long full[MAX_SLOTS];      // leader's copy is used: 2 CTAs x NUM_PROD_WARPS arrivals
   unsigned long long empty[MAX_SLOTS];     // 1 arrival (multicast tcgen05.commit)
-  unsigned long long tmem_full[2];         // 1 arrival (multicast tcgen05.commit)
-  unsigned long long tmem_empty[2];        // leader's copy: 2 CTAs x NUM_EPI_WARPS arrivals
+  unsigned long long tmem_full[NACC];      // 1 arrival (multicast tcgen05.commit)
+  unsigned long long tmem_empty[NACC];     // leader's copy: 2 CTAs x NUM_EPI_WARPS arrivals
   unsigned long long xchg_full[2];         // rank 0: 1 arrival + Npad*8 transaction bytes stored by rank 1 (st.async)
   unsigned long long xchg_empty[2];        // rank 1: one arrival per column thread of rank 0
   uint32_t tmem_base;
@@ -209,6 +212,7 @@ struct Params {
   int nslots;
   int slot_bytes;
   unsigned long long* prof;  // diagnostics: per-role cycle counters of cluster 0 (r4r_conv_debug_profile), or NULL
+  int lag;                   // slabs issued ahead of the one being published (1..MAX_LAG)
   const int* doc_len;        // [N] effective document lengths (r4r_doc_plan), or NULL = T for every document
   const int* doc_order;      // [N] processing order (longest first), or NULL = identity
 };
@@ -272,7 +276,7 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
   const int q = warp & 3, h = warp >> 2;
   const int row = q * 32 + lane;
   const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-  const uint32_t leader_tmem_empty[2] = {mapa(smem_u32(&ctl->tmem_empty[0]), 0), mapa(smem_u32(&ctl->tmem_empty[1]), 0)};
+  const uint32_t leader_tmem_empty0 = mapa(smem_u32(&ctl->tmem_empty[0]), 0);
   uint32_t it = 0, ndoc = 0;
   const bool prof_on = P.prof != nullptr && cluster_id == 0;
   long long w_full = 0, w_bar = 0, w_xchg = 0, t_begin = clock64();
@@ -291,7 +295,7 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
 #pragma unroll
     for (int c = 0; c < EC / 4; ++c) btile[c] = 0u;
     for (int pt = 0; pt < npt; ++pt, ++it) {
-      const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
+      const uint32_t buf = it % NACC, ph = (it / NACC) & 1u;
       TIMED_WAIT(w_full, mbar_wait(&ctl->tmem_full[buf], ph));
       tc_fence_after();
       const bool valid = (pt * 2 * TILE_M + (int)rank * TILE_M + row) < npos;
@@ -326,7 +330,7 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(leader_tmem_empty[buf]);
+      if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + buf * 8u);
     }
     // ---- per-document reduction over the warp's 32 rows: max value, smallest position on ties.
     // Two warp-wide reductions per column (redux.sync -> CREDUX): the maximum, then the smallest
@@ -397,6 +401,7 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
   }
 }
 
+template <int LAGT>
 __device__ __forceinline__ void producer_role(const Params& P, SharedCtl* ctl, uint8_t* ring, uint32_t rank, int cluster_id,
                                               int nclusters, int ptid) {
   const int spt = (P.Kc + CPS - 1) / CPS;                // slabs per tile
@@ -489,8 +494,8 @@ __device__ __forceinline__ void producer_role(const Params& P, SharedCtl* ctl, u
         }
         cp_async_commit();
         ++pending;
-        if (pending > (uint32_t)LAG) {
-          TIMED_WAIT(w_group, cp_async_wait<LAG>(); publish());
+        if (pending > (uint32_t)LAGT) {
+          TIMED_WAIT(w_group, cp_async_wait<LAGT>(); publish());
           --pending;
         }
         if (++slot == (uint32_t)nslots) { slot = 0; empty_parity ^= 1u; }
@@ -537,7 +542,7 @@ __device__ __forceinline__ void mma_role(const Params& P, SharedCtl* ctl, const 
     work_item(P, k, doc, Td);
     const int npt = tiles_of(Td);
     for (int pt = 0; pt < npt; ++pt, ++it) {
-      const uint32_t buf = it & 1u, use = it >> 1;
+      const uint32_t buf = it % NACC, use = it / NACC;
       TIMED_WAIT(w_tmem, mbar_wait(&ctl->tmem_empty[buf], (use & 1u) ^ 1u));       // both CTAs' epilogues drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = ctl->tmem_base + buf * ACC_STRIDE;
@@ -587,9 +592,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < MAX_SLOTS; ++i) { mbar_init(&ctl->full[i], 2 * NUM_PROD_WARPS); mbar_init(&ctl->empty[i], 1); }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NACC; ++i) {
       mbar_init(&ctl->tmem_full[i], 1);
       mbar_init(&ctl->tmem_empty[i], 2 * NUM_EPI_WARPS);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&ctl->xchg_full[i], 1);
       mbar_init(&ctl->xchg_empty[i], (uint32_t)P.Npad);
     }
@@ -623,7 +630,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
       default: epilogue_role<64>(P, ctl, rank, cluster_id, nclusters, warp, lane); break;
     }
   } else if (warp < MMA_WARP) {
-    producer_role(P, ctl, ring, rank, cluster_id, nclusters, threadIdx.x - NUM_EPI_WARPS * 32);
+    const int ptid = threadIdx.x - NUM_EPI_WARPS * 32;
+    switch (P.lag) {
+      case 1:  producer_role<1>(P, ctl, ring, rank, cluster_id, nclusters, ptid); break;
+      case 3:  producer_role<3>(P, ctl, ring, rank, cluster_id, nclusters, ptid); break;
+      case 4:  producer_role<4>(P, ctl, ring, rank, cluster_id, nclusters, ptid); break;
+      default: producer_role<2>(P, ctl, ring, rank, cluster_id, nclusters, ptid); break;
+    }
   } else if (rank == 0) {
     mma_role(P, ctl, bsm, ring, cluster_id, nclusters, lane);
   }
@@ -740,7 +753,13 @@ static int conv_pool_tc_launch(const void* shadow, int64_t V, int Epad, int E, i
   long long ns = avail / ((long long)CPS * RA * 16);
   if (ns > MAX_SLOTS) ns = MAX_SLOTS;
   const int nslots = (int)ns;
-  R4R_REQUIRE(nslots >= LAG + 2, R4R_EUNSUP, "conv_pool_tc: E=%d F=%d leaves no room for the A ring next to the filter bank", E, F);
+  int lag = LAG;
+  {
+    const char* e = getenv("R4R_CONV_LAG");                 // tuning override
+    if (e && atoi(e) >= 1 && atoi(e) <= MAX_LAG) lag = atoi(e);
+    if (lag > nslots - 2) lag = nslots - 2;
+  }
+  R4R_REQUIRE(nslots >= 3 && lag >= 1, R4R_EUNSUP, "conv_pool_tc: E=%d F=%d leaves no room for the A ring next to the filter bank", E, F);
   const int slot_bytes = CPS * RA * 16;
   const size_t smem_bytes = (size_t)(ctl_bytes + b_bytes + (long long)nslots * slot_bytes);
 
@@ -759,6 +778,7 @@ static int conv_pool_tc_launch(const void* shadow, int64_t V, int Epad, int E, i
   P.prof = g_prof;
   P.doc_len = doc_len;
   P.doc_order = doc_order;
+  P.lag = lag;
 
   R4R_CUDA(cudaFuncSetAttribute(conv_pool_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   long long nclusters = sm_count / 2;
