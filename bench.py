@@ -267,9 +267,8 @@ def run_b200(args):
     se_sum = torch.zeros(1, device=dev, dtype=torch.float32)
     conv_events = []
     ops.set_conv_event_sink(conv_events)
-    launches0 = _lib.launch_count
     steps_res = [CapturedStep(model, criterion, opt, d, y, se_sum, group, float(world)) for d, y in res.batches]
-    launches_per_step = (_lib.launch_count - launches0) // len(steps_res)
+    launches_per_step = steps_res[0].launches              # this library's kernels inside one captured step
     res_events = list(conv_events)
     ops.set_conv_event_sink(None)
 

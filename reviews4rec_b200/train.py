@@ -101,7 +101,8 @@ class CapturedStep:
         model.zero_grad(set_to_none=True)
         self.graph = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
-        from . import ops
+        from . import _lib, ops
+        launches0 = _lib.launch_count
         with torch.cuda.graph(self.graph):
             ops.arena_begin(dev)                    # one memset for all the zeroed gradient buffers of the step
             out = model(data)
@@ -115,6 +116,7 @@ class CapturedStep:
                 allreduce_dense_grads(model, group, int(grad_div))
             optimizer.step()
             ops.arena_end()
+        self.launches = _lib.launch_count - launches0       # kernels of this library one replay launches
         self.out = out
 
     def replay(self):

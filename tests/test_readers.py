@@ -162,3 +162,24 @@ def test_models_read_native_ragged_batches(mt):
     for a, b in zip(results[0][0], results[1][0]):
         assert torch.equal(a, b)
     assert abs(results[0][1] - results[1][1]) <= 1e-5 * abs(results[0][1])
+
+
+def test_ragged_idx_shape_logic_cpu():
+    """RaggedIdx is a shape-carrying handle: the reshapes the models perform (DeepCoNN.py:40-50, NARRE.py:91-100)
+    must keep the document length and share the buffers."""
+    from reviews4rec_b200.ops import RaggedIdx
+    tok = torch.arange(10, dtype=torch.int32)
+    off = torch.tensor([0, 2, 2, 5, 6, 8, 10], dtype=torch.int64)
+    r = RaggedIdx(tok, off, (2, 3, 7))                        # NARRE: [B, R, W]
+    assert r.dim() == 3 and r.numel() == 42 and tuple(r.shape) == (2, 3, 7)
+    f = r.reshape(6, 7)
+    assert tuple(f.shape) == (6, 7) and f.tokens is tok and f.offsets is off
+    assert tuple(r.reshape(6, -1).shape) == (6, 7) and tuple(f.reshape(2, 3, 7).shape) == (2, 3, 7)
+    with pytest.raises(RuntimeError):
+        r.reshape(3, 14)                                      # would merge documents
+    with pytest.raises(ValueError):
+        RaggedIdx(tok, off, (5, 7))                           # offsets do not describe 5 rows
+    with pytest.raises(TypeError):
+        RaggedIdx(tok.long(), off, (6, 7))
+    with pytest.raises(RuntimeError):
+        f.padded()                                            # no CPU fallback
