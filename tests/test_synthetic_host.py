@@ -1,0 +1,36 @@
+"""CPU checks of the benchmark's host side: the synthetic Amazon-shaped batches follow SURVEY.md 8(d), and the
+contract figures bench.py divides by are the ones SURVEY.md derives."""
+import numpy as np
+import torch
+
+
+def test_synthetic_batches_follow_the_survey_spec():
+    from reviews4rec_b200.synthetic import SyntheticReader
+    hp = {"model_type": "deepconn", "total_users": 1000000, "total_items": 100000, "input_length": 1000}
+    V, B = 50001, 512
+    r = SyntheticReader(hp, B, 2, V, seed=1234)
+    (data, y), (data2, _) = r.batches
+    assert [d is None for d in data] == [True, True, True, False, False, False, False]        # slots DeepCoNN does not read
+    ud, idoc, uid, iid = data[3], data[4], data[5], data[6]
+    assert ud.dtype == torch.int64 and tuple(ud.shape) == (B, 1000) and y.dtype == torch.float32
+    assert int(ud.min()) >= 0 and int(ud.max()) < V and int(uid.max()) < hp["total_users"] and int(iid.max()) < hp["total_items"]
+    docs = torch.cat([ud, idoc]).numpy()
+    lens = np.where((docs != 0).any(1), 1000 - np.argmax((docs != 0)[:, ::-1], axis=1), 0)
+    assert 230 <= np.median(lens) <= 380                       # log-normal, median 300
+    assert 0.55 <= float((lens < 1000).mean()) <= 0.95         # most documents carry a padding tail
+    assert 0.50 <= float((docs == 0).mean()) <= 0.70           # ~60 % of all positions are the padding token
+    body = docs[docs != 0]
+    assert float((body == 1).mean()) > 5 * float((body == 1000).mean())        # Zipf head
+    assert set(np.unique(y.numpy())) <= {1.0, 2.0, 3.0, 4.0, 5.0} and float((y == 5).float().mean()) > 0.4
+    assert not torch.equal(ud, data2[3])                       # batches differ
+    r2 = SyntheticReader(hp, B, 1, V, seed=1234)
+    assert torch.equal(r2.batches[0][0][3], ud)                # seeded
+
+
+def test_contract_figures():
+    import bench
+    hp = dict(bench.HP)
+    assert bench.algorithmic_bytes_per_rating(hp) == 2416024
+    assert abs(bench.conv_flops_per_doc(hp) - 180.36e6) < 0.01e6          # 2 * 1002 * 100 * 900
+    assert bench.V_WORDS == 50001 and hp["total_users"] == 1000000 and hp["total_items"] == 100000
+    assert hp["word_embed_size"] == 300 and hp["input_length"] == 1000 and hp["latent_size"] == 10
