@@ -312,3 +312,60 @@ class CsrReader:
     def iter(self, eval=False):
         for lo in range(0, self.total, self.bsz):
             yield self.batch(lo, min(self.total, lo + self.bsz))
+
+
+# ------------------------------------------------------------------------------------------ reference pickles
+def _load_pickle(path_without_ext):
+    import pickle
+    with open(path_without_ext + ".pkl", "rb") as f:                   # utils.py:23-25 load_obj
+        return pickle.load(f)
+
+
+def reference_pickles_to_arrays(data_dir: str) -> dict:
+    """Host side (numpy only) of ``load_data``: reads the pickles the reference's preprocessing writes
+    (data_scripts/preprocess_random_split.py:282-299: train / test / val = lists of [user, item, rating],
+    user_reviews, this_index_user_item, test_reviews, num_users_items) and returns the CSR arrays
+    ``ReviewStore`` / ``CsrReader`` take.  Train review n is the text of train rating n
+    (``user_reviews[u][this_index_user_item[u][i][0]]``, :213-218); held-out reviews come from
+    ``test_reviews[u][i]`` (:228-243), ``[0]`` when missing (data.py:239-241)."""
+    train = _load_pickle(data_dir + "train")
+    user_reviews = _load_pickle(data_dir + "user_reviews")
+    this_index = _load_pickle(data_dir + "this_index_user_item")
+    test_reviews = _load_pickle(data_dir + "test_reviews")
+    num_users, num_items, num_words = _load_pickle(data_dir + "num_users_items")
+    out = {"total_users": int(num_users), "total_items": int(num_items), "total_words": int(num_words)}
+
+    def ratings(rows):
+        a = np.asarray([[r[0], r[1]] for r in rows], dtype=np.int64).reshape(-1, 2)
+        return a[:, 0].copy(), a[:, 1].copy(), np.asarray([r[2] for r in rows], dtype=np.float32)
+
+    def csr(reviews):
+        lens = np.fromiter((len(r) for r in reviews), dtype=np.int64, count=len(reviews))
+        tok = np.fromiter((t for r in reviews for t in r), dtype=np.int64, count=int(lens.sum()))
+        if tok.size and (tok.min() < 0 or tok.max() >= 2 ** 31):
+            raise ValueError("token ids must fit in int32")
+        return tok.astype(np.int32), np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+
+    tu, ti, ty = ratings(train)
+    out["train_user"], out["train_item"], out["train_y"] = tu, ti, ty
+    out["tok"], out["rev_off"] = csr([user_reviews[int(u)][this_index[int(u)][int(i)][0]] for u, i in zip(tu, ti)])
+    for split in ("test", "val"):
+        u, i, y = ratings(_load_pickle(data_dir + split))
+        held = [test_reviews.get(int(a), {}).get(int(b), [0]) for a, b in zip(u, i)]
+        out[split + "_user"], out[split + "_item"], out[split + "_y"] = u, i, y
+        out[split + "_tok"], out[split + "_off"] = csr(held)
+    return out
+
+
+def load_data(hyper_params: dict, device="cuda"):
+    """``data.load_data(hyper_params)`` (data.py:449-482) over device-resident reviews: returns
+    ``(train_reader, test_reader, val_reader, hyper_params)`` with ``total_users / total_items / total_words``
+    filled in like the reference (:468-470).  Ranking negatives (``iter_negs``) are not loaded."""
+    a = reference_pickles_to_arrays(hyper_params["data_dir"])
+    for k in ("total_users", "total_items", "total_words"):
+        hyper_params[k] = a[k]
+    store = ReviewStore(a["tok"], a["rev_off"], a["train_user"], a["train_item"], a["total_users"], a["total_items"], device)
+    train = CsrReader(hyper_params, store, a["train_y"], train=True)
+    test, val = (CsrReader(hyper_params, store, a[s + "_y"], train=False, users=a[s + "_user"], items=a[s + "_item"],
+                           this_tok=a[s + "_tok"], this_off=a[s + "_off"]) for s in ("test", "val"))
+    return train, test, val, hyper_params

@@ -108,3 +108,63 @@ def test_review_list_side_matches_this_index_user_item():
             assert got == lists[l] and nb[ptr[l]:ptr[l + 1]].tolist() == nbmap[l]
         for n in range(len(tu)):
             assert int(rank[n]) == this_index[int(tu[n])][int(ti[n])][col]
+
+
+def _write_reference_pickles(tmp, z, U, I):
+    """The files data_scripts/preprocess_random_split.py:282-299 writes, for the golden dataset."""
+    import pickle
+    revs = split_reviews(z["tok"], z["rev_off"])
+    user_reviews = {u: [] for u in range(U)}
+    item_reviews = {i: [] for i in range(I)}
+    this_index = {}
+    train = []
+    for u, i, y, rev in zip(z["train_user"].tolist(), z["train_item"].tolist(), z["train_y"].tolist(), revs):
+        this_index.setdefault(u, {})[i] = [len(user_reviews[u]), len(item_reviews[i])]
+        user_reviews[u].append(rev)
+        item_reviews[i].append(rev)
+        train.append([u, i, y])
+    erevs = split_reviews(z["eval_tok"], z["eval_off"])
+    test_reviews, rows = {}, []
+    for u, i, y, rev in zip(z["eval_user"].tolist(), z["eval_item"].tolist(), z["eval_y"].tolist(), erevs):
+        test_reviews.setdefault(u, {})[i] = rev
+        rows.append([u, i, y])
+    objs = {"train": train, "test": rows[:4], "val": rows[4:], "user_reviews": user_reviews, "item_reviews": item_reviews,
+            "this_index_user_item": this_index, "test_reviews": test_reviews, "num_users_items": [U, I, 59]}
+    for name, obj in objs.items():
+        with open(os.path.join(tmp, name + ".pkl"), "wb") as f:
+            pickle.dump(obj, f, 2)
+    return rows
+
+
+def test_reference_pickles_to_arrays(tmp_path):
+    """Host side of readers.load_data (CPU): the reference's pickles become exactly the CSR arrays the golden
+    dataset was generated from."""
+    from reviews4rec_b200.readers import reference_pickles_to_arrays
+    z, hp, (U, I, V) = load_docs_golden("deepconn")
+    rows = _write_reference_pickles(str(tmp_path), z, U, I)
+    a = reference_pickles_to_arrays(str(tmp_path) + "/")
+    assert (a["total_users"], a["total_items"], a["total_words"]) == (U, I, 59)
+    for k in ("tok", "rev_off", "train_user", "train_item", "train_y"):
+        assert np.array_equal(a[k], z[k]) and a[k].dtype == z[k].dtype, k
+    got_u = np.concatenate([a["test_user"], a["val_user"]])
+    got_tok = np.concatenate([a["test_tok"], a["val_tok"]])
+    got_off = np.concatenate([a["test_off"], a["val_off"][1:] + a["test_off"][-1]])
+    assert np.array_equal(got_u, z["eval_user"]) and np.array_equal(got_tok, z["eval_tok"]) and np.array_equal(got_off, z["eval_off"])
+    assert len(a["test_y"]) == 4 and len(a["val_y"]) == len(rows) - 4
+
+
+@pytest.mark.gpu
+def test_load_data_from_reference_pickles(tmp_path):
+    """readers.load_data == data.load_data over device-resident reviews: the train reader yields the golden
+    batches of the reference reader."""
+    from reviews4rec_b200.readers import load_data
+    z, hp, (U, I, V) = load_docs_golden("deepconn")
+    _write_reference_pickles(str(tmp_path), z, U, I)
+    hp = dict(hp, data_dir=str(tmp_path) + "/")
+    train, test, val, hp2 = load_data(hp, "cuda")
+    assert hp2["total_users"] == U and hp2["total_items"] == I and len(train) == int(z["train.nb"][0])
+    for b, (data, y) in enumerate(train.iter()):
+        for j, d in enumerate(data):
+            assert np.array_equal(d.cpu().numpy(), z["train.b%d.d%d" % (b, j)]), (b, j)
+    n_eval = sum(int(y.shape[0]) for _, y in test.iter()) + sum(int(y.shape[0]) for _, y in val.iter())
+    assert n_eval == len(z["eval_y"])
