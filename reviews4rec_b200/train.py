@@ -78,6 +78,55 @@ def train(model, criterion, optimizer, reader, hyper_params):
     return metrics
 
 
+def train_complete(hyper_params, Model, train_reader, val_reader, user_count, item_count, model, review=True,
+                   optim_cls=None):
+    """``main.train_complete`` (main.py:73-136): MSELoss, Adam (or the four TransNet optimizers of
+    utils.init_transnet_optim), ``hyper_params['epochs']`` epochs of train -> validate -> log, the state_dict with
+    the best validation MSE saved to ``hyper_params['model_path']``, and that checkpoint reloaded into a fresh
+    ``Model(hyper_params)`` which is returned in eval mode.  ``optim_cls`` defaults to this package's FusedAdam
+    (same constructor arguments and semantics as the reference's torch.optim.Adam)."""
+    import datetime as dt
+    import time
+
+    from .eval import evaluate
+    from .loss import MSELoss
+    from .optim import FusedAdam
+    from .utils import file_write, init_transnet_optim, log_end_epoch
+
+    optim_cls = optim_cls or FusedAdam
+    log = hyper_params["log_file"]
+    file_write(log, "\n\nSimulation run on: " + str(dt.datetime.now()) + "\n\n")
+    file_write(log, "Data reading complete!")
+    file_write(log, "Number of train batches: {:4d}".format(len(train_reader)))
+    file_write(log, "Number of validation batches: {:4d}".format(len(val_reader)))
+    criterion = MSELoss(hyper_params)
+    if hyper_params["model_type"] in TRANSNET:
+        optimizer = init_transnet_optim(hyper_params, model, optim_cls)
+    else:
+        optimizer = optim_cls(model.parameters(), lr=hyper_params["lr"], weight_decay=hyper_params["weight_decay"])
+    file_write(log, str(model))
+    file_write(log, "\nModel Built!\nStarting Training...\n")
+    device = next(model.parameters()).device
+    try:
+        best_mse = float("inf")
+        for epoch in range(1, hyper_params["epochs"] + 1):
+            t0 = time.time()
+            metrics = train(model, criterion, optimizer, train_reader, hyper_params)
+            metrics, _, _ = evaluate(model, criterion, val_reader, hyper_params, user_count, item_count, review=review)
+            metrics["dataset"] = hyper_params.get("dataset")
+            log_end_epoch(hyper_params, metrics, epoch, time.time() - t0, metrics_on="(VAL)")
+            if metrics["MSE"] < best_mse:                       # main.py:122-126
+                print("Saving model...")
+                torch.save(model.state_dict(), hyper_params["model_path"])
+                best_mse = metrics["MSE"]
+    except KeyboardInterrupt:
+        print("Exiting from training early")
+    best = Model(hyper_params).to(device)                       # main.py:131-134
+    best.load_state_dict(torch.load(hyper_params["model_path"], map_location=device))
+    best.eval()
+    return best
+
+
 class CapturedStep:
     """One non-TransNet training batch of ``train()`` -- zero_grad, forward, per-sample SE, backward
     of the mean, optional data-parallel gradient all-reduce, optimizer step (main.py:26-60) --

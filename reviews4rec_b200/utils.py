@@ -27,3 +27,25 @@ def init_transnet_optim(hyper_params, model, optim_cls=torch.optim.Adam):
         fm_params += [model.user_embedding.weight, model.item_embedding.weight]
     return [optim_cls(model.source.parameters(), **kw), optim_cls(fm_params, **kw),
             optim_cls(model.target.parameters(), **kw), optim_cls(model.parameters(), **kw)]
+
+
+def file_write(log_file, s, dont_print=False):
+    """utils.py:36-40 -- append a line to the run's log file (and echo it)."""
+    if not dont_print:
+        print(s)
+    with open(log_file, "a") as f:
+        f.write(s + "\n")
+
+
+def log_end_epoch(hyper_params, metrics, epoch, time_elapsed, metrics_on="(VAL)"):
+    """utils.py:53-63 -- the reference's end-of-epoch banner, same text."""
+    string2 = ""
+    for m in metrics:
+        string2 += " | " + m + " = " + str(metrics[m])
+    string2 += " " + metrics_on
+    ss = "-" * 89
+    ss += "\n| end of epoch {} | time: {:5.2f}s".format(epoch, time_elapsed)
+    ss += string2
+    ss += "\n"
+    ss += "-" * 89
+    file_write(hyper_params["log_file"], ss)
