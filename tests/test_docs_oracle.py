@@ -151,20 +151,3 @@ def test_reference_pickles_to_arrays(tmp_path):
     got_off = np.concatenate([a["test_off"], a["val_off"][1:] + a["test_off"][-1]])
     assert np.array_equal(got_u, z["eval_user"]) and np.array_equal(got_tok, z["eval_tok"]) and np.array_equal(got_off, z["eval_off"])
     assert len(a["test_y"]) == 4 and len(a["val_y"]) == len(rows) - 4
-
-
-@pytest.mark.gpu
-def test_load_data_from_reference_pickles(tmp_path):
-    """readers.load_data == data.load_data over device-resident reviews: the train reader yields the golden
-    batches of the reference reader."""
-    from reviews4rec_b200.readers import load_data
-    z, hp, (U, I, V) = load_docs_golden("deepconn")
-    _write_reference_pickles(str(tmp_path), z, U, I)
-    hp = dict(hp, data_dir=str(tmp_path) + "/")
-    train, test, val, hp2 = load_data(hp, "cuda")
-    assert hp2["total_users"] == U and hp2["total_items"] == I and len(train) == int(z["train.nb"][0])
-    for b, (data, y) in enumerate(train.iter()):
-        for j, d in enumerate(data):
-            assert np.array_equal(d.cpu().numpy(), z["train.b%d.d%d" % (b, j)]), (b, j)
-    n_eval = sum(int(y.shape[0]) for _, y in test.iter()) + sum(int(y.shape[0]) for _, y in val.iter())
-    assert n_eval == len(z["eval_y"])

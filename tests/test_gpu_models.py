@@ -221,29 +221,3 @@ def test_captured_step_equals_eager_training(mt):
         # same tolerances as the reference train-loop test: atomics make the gradient summation order vary
         atol = hp["lr"] * 3 * dims["NB"] if (mt == "NARRE" and k.startswith("attention_scorer_") and k.endswith(".3.bias")) else 4e-6
         assert_close(b[k], a[k], rtol=1e-4, atol=atol, msg="%s %s" % (mt, k))
-
-
-@pytest.mark.gpu
-def test_train_complete_keeps_the_best_validation_checkpoint(tmp_path):
-    """main.train_complete's contract (main.py:73-136): epochs of train -> validate, best-on-validation state_dict
-    saved and reloaded into a fresh Model returned in eval mode; the log file carries the epoch banners."""
-    import reviews4rec_b200 as R
-    from reviews4rec_b200.eval import evaluate
-    from reviews4rec_b200.train import train_complete
-    mt = "deepconn"
-    z, dims = load_golden(mt)
-    model, hp = build(mt, z, dims)
-    hp.update(epochs=3, log_file=str(tmp_path / "log.txt"), model_path=str(tmp_path / "model.pt"), dataset="golden")
-    batches = golden_batches(z, dims, "cuda")
-    train_reader, val_reader = ListReader(batches[:2]), ListReader(batches[2:])
-    best = train_complete(hp, R.DeepCoNN, train_reader, val_reader, {}, {}, model, review=True)
-    assert isinstance(best, R.DeepCoNN) and not best.training and next(best.parameters()).is_cuda
-    log = open(hp["log_file"]).read()
-    assert log.count("| end of epoch") == 3 and "(VAL)" in log and "Number of train batches:    2" in log
-    # the returned model is the checkpoint on disk, and its validation MSE is the smallest one logged
-    saved = torch.load(hp["model_path"], map_location="cuda")
-    for k, v in best.state_dict().items():
-        assert torch.equal(v, saved[k])
-    logged = [float(line.split("MSE = ")[1].split(" ")[0]) for line in log.splitlines() if "| end of epoch" in line]
-    m, _, _ = evaluate(best, R.MSELoss(hp), val_reader, hp, {}, {}, True)
-    assert abs(m["MSE"] - min(logged)) < 1e-4
