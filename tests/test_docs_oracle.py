@@ -151,3 +151,31 @@ def test_reference_pickles_to_arrays(tmp_path):
     got_off = np.concatenate([a["test_off"], a["val_off"][1:] + a["test_off"][-1]])
     assert np.array_equal(got_u, z["eval_user"]) and np.array_equal(got_tok, z["eval_tok"]) and np.array_equal(got_off, z["eval_off"])
     assert len(a["test_y"]) == 4 and len(a["val_y"]) == len(rows) - 4
+
+
+def test_load_data_wiring_cpu(tmp_path, monkeypatch):
+    """readers.load_data's host wiring (what goes into ReviewStore / CsrReader), with the device classes replaced
+    by recorders -- the device end is covered by tests/test_z_host_mirrors.py on the GPU."""
+    from reviews4rec_b200 import readers
+    z, hp, (U, I, V) = load_docs_golden("deepconn")
+    _write_reference_pickles(str(tmp_path), z, U, I)
+    made = {}
+
+    class Store:
+        def __init__(self, tok, rev_off, tu, ti, total_users, total_items, device):
+            made["store"] = (tok, rev_off, tu, ti, total_users, total_items, device)
+
+    class Reader:
+        def __init__(self, hyper_params, store, ratings, train, users=None, items=None, this_tok=None, this_off=None):
+            made.setdefault("readers", []).append((train, len(ratings), None if users is None else len(users),
+                                                    None if this_off is None else len(this_off)))
+
+    monkeypatch.setattr(readers, "ReviewStore", Store)
+    monkeypatch.setattr(readers, "CsrReader", Reader)
+    hp = dict(hp, data_dir=str(tmp_path) + "/")
+    train, test, val, hp2 = readers.load_data(hp, "cuda:0")
+    assert hp2 is hp and (hp["total_users"], hp["total_items"], hp["total_words"]) == (U, I, 59)
+    tok, rev_off, tu, ti, nu, ni, dev = made["store"]
+    assert np.array_equal(tok, z["tok"]) and np.array_equal(rev_off, z["rev_off"]) and (nu, ni, dev) == (U, I, "cuda:0")
+    n_eval = len(z["eval_y"])
+    assert made["readers"] == [(True, len(z["train_y"]), None, None), (False, 4, 4, 5), (False, n_eval - 4, n_eval - 4, n_eval - 3)]
