@@ -15,6 +15,7 @@ ops, fp32 by default, fp64 on request) of what the reference's ``nn.Module`` cla
   ``torch_fm``           ``pytorch_models/common_pytorch_models.py:49-57``
   ``deepconn_forward``   ``pytorch_models/DeepCoNN.py:37-72``
   ``mf_forward``         ``pytorch_models/MF.py:39-68``
+  ``neumf_forward``      ``pytorch_models/NeuMF.py:23-36,59-73,114-138`` (GMF / MLP / NeuMF), ``neumf_init`` ``:93-112``
   ``narre_forward``      ``pytorch_models/NARRE.py:53-124``
   ``transnet_forward``   ``pytorch_models/TransNet.py:25-37,55-61,83-122``
   ``adam_step``          ``torch.optim.Adam`` as configured at ``main.py:94-96`` / ``utils.py:70-92``
@@ -223,8 +224,54 @@ def transnet_forward(P: Params, data: Sequence, hp: dict, train: bool = False,
             ((s_ir - t_ir) ** 2).sum(-1).mean()]
 
 
+def neumf_forward(P: Params, data: Sequence, hp: dict, train: bool = False,
+                  masks: Optional[dict] = None) -> torch.Tensor:
+    """GMF / MLP / NeuMF forward, pytorch_models/NeuMF.py:23-36, :59-73, :114-138 (``model_type`` 'GMF', 'MLP',
+    'NeuMF').  ``masks`` keys: 'user','item' (GMF part), 'mlp_user','mlp_item','project'."""
+    masks = masks or {}
+    mt, p = hp["model_type"], hp["dropout"]
+    user_id, item_id = data[5], data[6]
+    shape = user_id.shape
+    uid, iid = user_id.reshape(-1), item_id.reshape(-1)
+    bias = P["user_bias"].gather(0, uid).reshape(shape) + P["item_bias"].gather(0, iid).reshape(shape) + P["global_bias"]
+    emb = lambda k, ids, m: _drop(P[k + ".weight"].index_select(0, ids), p, train, masks.get(m))
+
+    def project(x):
+        x = _drop(x, p, train, masks.get("project"))
+        return F.linear(F.relu(F.linear(x, P["project.1.weight"], P["project.1.bias"])), P["project.3.weight"], P["project.3.bias"])
+
+    if mt == "GMF":
+        joint = emb("user_embedding", uid, "user") * emb("item_embedding", iid, "item")
+    elif mt == "MLP":
+        joint = project(torch.cat([emb("user_embedding", uid, "user"), emb("item_embedding", iid, "item")], dim=-1))
+    else:
+        gmf = emb("gmf_user_embedding", uid, "user") * emb("gmf_item_embedding", iid, "item")
+        mlp = project(torch.cat([emb("mlp_user_embedding", uid, "mlp_user"), emb("mlp_item_embedding", iid, "mlp_item")], dim=-1))
+        joint = torch.cat([gmf, mlp], dim=-1)
+    rating = F.linear(joint, P["final.weight"], P["final.bias"])[:, 0].reshape(shape)
+    return bias + rating
+
+
+def neumf_init(gmf: Params, mlp: Params, neumf: Params) -> Params:
+    """NeuMF.init, pytorch_models/NeuMF.py:93-112."""
+    out = {k: v.clone() for k, v in neumf.items()}
+    out["gmf_user_embedding.weight"] = gmf["user_embedding.weight"].clone()
+    out["gmf_item_embedding.weight"] = gmf["item_embedding.weight"].clone()
+    out["mlp_user_embedding.weight"] = mlp["user_embedding.weight"].clone()
+    out["mlp_item_embedding.weight"] = mlp["item_embedding.weight"].clone()
+    for k in ("project.1.weight", "project.1.bias", "project.3.weight", "project.3.bias"):
+        out[k] = mlp[k].clone()
+    out["final.weight"] = torch.cat([gmf["final.weight"], mlp["final.weight"]], dim=-1)
+    out["final.bias"] = 0.5 * (gmf["final.bias"] + mlp["final.bias"])
+    out["user_bias"] = 0.5 * (gmf["user_bias"] + mlp["user_bias"])
+    out["item_bias"] = 0.5 * (gmf["item_bias"] + mlp["item_bias"])
+    return out
+
+
 def forward(P: Params, data: Sequence, hp: dict, train: bool = False, masks: Optional[dict] = None):
     mt = hp["model_type"]
+    if mt in ("GMF", "MLP", "NeuMF"):
+        return neumf_forward(P, data, hp, train, masks)
     if mt in ("deepconn", "deepconn++"):
         return deepconn_forward(P, data, hp, train, masks)
     if mt in ("bias_only", "MF", "MF_dot"):

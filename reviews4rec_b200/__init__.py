@@ -11,6 +11,7 @@ from .loss import MSELoss  # noqa: F401
 from .pytorch_models.DeepCoNN import DeepCoNN  # noqa: F401
 from .pytorch_models.MF import MF  # noqa: F401
 from .pytorch_models.NARRE import NARRE  # noqa: F401
+from .pytorch_models.NeuMF import GMF, MLP, NeuMF  # noqa: F401
 from .pytorch_models.TransNet import TransNet  # noqa: F401
 
-__all__ = ["DeepCoNN", "MF", "NARRE", "TransNet", "MSELoss"]
+__all__ = ["DeepCoNN", "MF", "NARRE", "TransNet", "GMF", "MLP", "NeuMF", "MSELoss"]

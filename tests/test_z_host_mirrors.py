@@ -52,3 +52,48 @@ def test_train_complete_keeps_the_best_validation_checkpoint(tmp_path):
     logged = [float(line.split("MSE = ")[1].split(" ")[0]) for line in log.splitlines() if "| end of epoch" in line]
     m, _, _ = evaluate(best, R.MSELoss(hp), val_reader, hp, {}, {}, True)
     assert abs(m["MSE"] - min(logged)) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["GMF", "MLP", "NeuMF"])
+def test_neumf_family_vs_reference(name):
+    """GMF / MLP / NeuMF drop-ins against the reference's forward and 3-batch main.train run."""
+    import reviews4rec_b200 as R
+    from reviews4rec_b200.optim import FusedAdam
+    from reviews4rec_b200.train import train
+    from tests.helpers import assert_close
+    from tests.test_neumf import batches, load_neumf, state
+    z, hp, NB = load_neumf()
+    hp = dict(hp, model_type=name)
+    model = getattr(R, name)(hp)
+    model.load_state_dict(state(z, name, "init"))
+    model = model.cuda()
+    bs = batches(z, NB, "cuda")
+    rank = [None] * 5 + [torch.from_numpy(z["rank.d5"]).cuda(), torch.from_numpy(z["rank.d6"]).cuda()]
+    model.eval()
+    with torch.no_grad():
+        assert_close(model(bs[0][0]), z["%s.eval.b0" % name], rtol=1e-4, atol=1e-6, msg="eval b0")
+        assert_close(model(rank), z["%s.eval.rank" % name], rtol=1e-4, atol=1e-6, msg="eval rank")
+    opt = FusedAdam(model.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"])
+    metrics = train(model, R.MSELoss(hp), opt, ListReader(bs), hp)
+    assert abs(metrics["MSE"] - float(z["%s.metric.MSE" % name][0])) <= 1e-4
+    sd = model.state_dict()
+    for k, v in state(z, name, "final").items():
+        assert_close(sd[k], v, rtol=1e-4, atol=4e-6, msg="%s final.%s" % (name, k))
+
+
+@pytest.mark.gpu
+def test_neumf_init_fuses_the_pretrained_models():
+    import reviews4rec_b200 as R
+    from tests.test_neumf import load_neumf, state
+    z, hp, NB = load_neumf()
+    gmf, mlp, neu = R.GMF(dict(hp, model_type="GMF")), R.MLP(dict(hp, model_type="MLP")), R.NeuMF(dict(hp, model_type="NeuMF"))
+    gmf.load_state_dict(state(z, "GMF", "final"))
+    mlp.load_state_dict(state(z, "MLP", "final"))
+    gmf, mlp, neu = gmf.cuda(), mlp.cuda(), neu.cuda()
+    neu.init(gmf, mlp)
+    want = state(z, "NeuMF", "init")
+    sd = neu.state_dict()
+    for k in want:
+        if k != "global_bias":
+            assert torch.equal(sd[k].cpu(), want[k]), k
