@@ -430,10 +430,13 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": value, "unit": "ratings/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"f16": "f16 operands / f32 accumulate", "bf16": "bf16 operands / f32 accumulate", "exact": "f32"}[args.conv_mode],
+        "dtype": {"f16": "f16", "bf16": "bf16", "exact": "f32"}[args.conv_mode],
         "data": "synthetic",
         "config": {"workload": "DeepCoNN E=300 F=100 T=1000 L=10 V=50001 U=1M I=100k (BASELINE configs[1])",
                    "batch_per_gpu": B, "global_batch": B * world, "conv_mode": args.conv_mode, "dropout": hp["dropout"],
+                   "arithmetic": {"f16": "conv operands f16 (private shadow of the frozen word table + packed filters), fp32 accumulation in TMEM; everything else fp32",
+                                  "bf16": "conv operands bf16, fp32 accumulation in TMEM; everything else fp32",
+                                  "exact": "fp32 everywhere (CUDA-core conv)"}[args.conv_mode],
                    "parallelism": parallelism,
                    "documents": ("ragged on the device (ops.RaggedIdx: int32 tokens before each trailing padding run + offsets); "
                                  "same padded documents as the reference's reader, never materialised") if ragged
