@@ -26,15 +26,27 @@
 // Warp roles per CTA (416 threads, 1 CTA/SM, persistent over documents):
 //   warps 0-7   epilogue : tcgen05.ld of this CTA's 128 x N accumulator (warp w: TMEM lane quarter
 //                          w&3, column half w>>2) -> running max / tile-of-max in registers across
-//                          the tiles of a document -> warp-shuffle + smem reduction per document ->
-//                          the two CTAs' partial (max, argmax) are merged through distributed
-//                          shared memory (rank 1 stores into rank 0) -> bias, ReLU, store
-//   warps 8-11  producer : cp.async.ca 16-byte gathers of the shadow-table rows into the A ring
-//                          (zero-fill for the conv padding rows); token ids are fetched one tile
-//                          ahead; one mbarrier arrival per warp per slab on the LEADER's barrier
-//   warp  12    MMA      : allocates TMEM (both CTAs); in the leader CTA one elected lane issues
-//                          tcgen05.mma, multicast tcgen05.commit releases ring slots ("empty") and
-//                          publishes accumulators ("tmem_full") in both CTAs
+//                          the tiles of a document -> per document two redux.sync per column (max,
+//                          then the smallest tile<<5|lane key among its holders = FIRST maximum) +
+//                          a four-warp shared-memory merge -> the two CTAs' partial (max, argmax)
+//                          are merged through distributed shared memory (rank 1 stores into rank 0
+//                          with st.async) -> bias, ReLU, store
+//   warps 8-11  producer : cp.async.ca 16-byte gathers of the shadow-table rows into a ring of
+//                          K=64 slabs (8 chunk columns: each lane owns one column and nine rows, so a
+//                          copy's address is a per-row base + a compile-time offset); conv padding
+//                          rows read the all-zero row V of the shadow table; token ids are fetched
+//                          one tile ahead and document descriptors one document ahead; one mbarrier
+//                          arrival per warp per slab on the LEADER's barrier, `lag` slabs after issue
+//   warp  12    MMA      : allocates all 512 TMEM columns (both CTAs) = four accumulator buffers; in
+//                          the leader CTA one elected lane issues tcgen05.mma, multicast
+//                          tcgen05.commit releases ring slots ("empty") and publishes accumulators
+//                          ("tmem_full") in both CTAs
+//
+// Work plan (docplan.cu): documents end in a run of one repeated padding token; every conv window
+// inside the run repeats a value max-pooling has already seen, so document n is processed as if it had
+// doc_len[n] = min(T, run start + 3) rows and arg-max positions >= doc_len are mapped back by
+// + (T - doc_len) -- bit-identical results, ~2.5x less work on Amazon-shaped batches -- and documents
+// are issued longest first.  Ragged input (tokens + offsets instead of padded ids) takes the same path.
 //
 // L1-allocating gathers matter: ~2/3 of all positions of Amazon-shaped documents are the pad token
 // and the rest is Zipfian, so with L2-only (cp.async.cg) loads all SMs queue on a handful of L2
