@@ -34,3 +34,42 @@ def test_train_complete_control_flow(tmp_path, monkeypatch):
     assert best.w.tolist() == [2.0, 2.0, 2.0]                # epoch 2's weights, reloaded from the checkpoint
     log = open(hp["log_file"]).read()
     assert log.count("| end of epoch") == 4 and "Number of train batches:    3" in log and "MSE = 1.5" in log
+
+
+def test_main_drivers_control_flow(tmp_path, monkeypatch):
+    """main_pytorch / main_NeuMF / main (main.py:289-431): call order and hand-offs, with the device work replaced
+    by recorders."""
+    import pickle
+    import reviews4rec_b200.main as M
+    for name in ("user_count", "item_count"):
+        with open(tmp_path / (name + ".pkl"), "wb") as f:
+            pickle.dump({1: 2}, f, 2)
+    log = []
+    monkeypatch.setattr(M, "load_data", lambda hp, device: ("TRAIN", "TEST", "VAL", hp))
+    monkeypatch.setattr(M, "xavier_init", lambda m: log.append(("xavier", type(m).__name__)))
+    monkeypatch.setattr(M, "model_class", lambda mt: Tiny)
+
+    def fake_train_complete(hp, Model, tr_, va, uc, ic, model, review=True):
+        log.append(("train_complete", Model.__name__, hp["model_path"], tr_, va, review))
+        return model
+
+    monkeypatch.setattr(M, "train_complete", fake_train_complete)
+    monkeypatch.setattr(M, "evaluate", lambda model, crit, reader, hp, uc, ic, review: ({"MSE": 1.25}, {0: [1.0]}, {0: [1.0]}))
+    hp = {"model_type": "deepconn", "data_dir": str(tmp_path) + "/", "model_path": str(tmp_path / "m.pt"),
+          "log_file": str(tmp_path / "log.txt"), "lr": 0.1, "weight_decay": 0.0}
+    assert M.main(dict(hp), gpu_id=None, device="cpu") == {"MSE": 1.25}
+    assert log == [("xavier", "Tiny"), ("train_complete", "Tiny", hp["model_path"], "TRAIN", "VAL", True)]
+    assert "| end of epoch final" in open(hp["log_file"]).read()
+    import pytest
+    with pytest.raises(ValueError):
+        M.main(dict(hp, model_type="HFT"))
+
+    # NeuMF: GMF and MLP pre-trained under <path>_gmf / <path>_mlp, fused, then NeuMF under <path>
+    import reviews4rec_b200.pytorch_models.NeuMF as N
+    log.clear()
+    for cls in ("GMF", "MLP", "NeuMF"):
+        monkeypatch.setattr(N, cls, type(cls, (Tiny,), {"init": lambda self, a, b: log.append(("init", type(a).__name__, type(b).__name__))}))
+    M.main(dict(hp, model_type="NeuMF"), device="cpu")
+    steps = [e for e in log if e[0] in ("train_complete", "init")]
+    assert [s[1] for s in steps] == ["GMF", "MLP", "GMF", "NeuMF"] and steps[2] == ("init", "GMF", "MLP")
+    assert steps[0][2].endswith("_gmf") and steps[1][2].endswith("_mlp") and steps[3][2] == hp["model_path"] and steps[3][5] is True
