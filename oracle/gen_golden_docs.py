@@ -85,6 +85,23 @@ def run(model_type, out_path):
                 out["%s.b%d.d%d" % (split, b, j)] = np.array(d, dtype=np.int64)
             out["%s.b%d.y" % (split, b)] = np.array(y, dtype=np.float32)
         out["%s.nb" % split] = np.array([b + 1], dtype=np.int64)
+        if split == "eval":
+            # ranking candidates (data.py:375-447 iter_negs): per user the positive item + 5 sampled negatives, in the
+            # format data_scripts/make_negative_sets.py writes: negs[user] = [[positive], [negatives]]
+            rng = np.random.default_rng(5)
+            negs = {}
+            for u, i, _, _ in rows:
+                if u not in negs and len(negs) < 5:
+                    negs[u] = [[i], [int(x) for x in rng.choice(I, 5, replace=False)]]
+            ur, ir = copy.deepcopy(user_reviews), copy.deepcopy(item_reviews)
+            nl = refdata.DataLoader(hp, [r[:3] for r in rows], ur, ir, negs, train_loader=train_loader, **kw)
+            out["negs.users"] = np.array(list(negs), dtype=np.int64)
+            out["negs.items"] = np.array([negs[u][0] + negs[u][1] for u in negs], dtype=np.int64)
+            for b, (data, y) in enumerate(nl.iter_negs(True)):
+                for j, d in enumerate(data):
+                    out["negs.b%d.d%d" % (b, j)] = d.numpy().astype(np.int64)
+                out["negs.b%d.y" % b] = y.numpy().astype(np.float32)
+            out["negs.nb"] = np.array([b + 1], dtype=np.int64)
     np.savez_compressed(out_path, **out)
     print(out_path, {k: v.shape for k, v in out.items() if k.startswith("train.b0")})
 

@@ -16,6 +16,8 @@ tests/test_docs_oracle.py replays them through this file.
                           to narre_num_reviews with all-zero reviews)
   ``batches``             data.py:251-337 ``iter_review`` (neighbour lists padded with total_users + 1 /
                           total_items + 1 to 10 and cut to 10, :277-282)
+  ``batches_negs``        data.py:375-447 ``iter_negs`` (ranking candidates: the positive item + the sampled
+                          negatives of every user in ``negs``; inputs shaped [bsz, 1+5, ...])
   ======================  =========================================================================
 """
 from typing import Dict, List, Optional, Sequence
@@ -87,3 +89,31 @@ def batches(users, items, ratings, lists, hp: dict, train: bool, test_reviews: O
             for slot, v in zip(acc, (this, who, what, u_r, i_r, u, i)):
                 slot.append(v)
         yield [join(acc[0]), acc[1], acc[2], join(acc[3]), join(acc[4]), acc[5], acc[6]], [float(r) for r in ratings[lo:lo + B]]
+
+
+def batches_negs(neg_users, neg_items, lists, hp: dict, test_review_of):
+    """``iter_negs(review=True)`` of an evaluation reader (data.py:375-447).  ``neg_items[m]`` = [positive] +
+    negatives of user ``neg_users[m]`` (make_negative_sets.py); ``test_review_of(u, i)`` = held-out review or None.
+    Every candidate i2 gets the user's whole document and i2's whole document, but -- as in the reference, which
+    calls ``remove_overlap(u_r, i_r, u, i)`` with the POSITIVE item -- the held-out review and the
+    users-who-reviewed list are the positive item's for all candidates."""
+    user_reviews, item_reviews, _, u_to_i, i_to_u = lists
+    B = int(hp["batch_size"])
+    narre = hp["model_type"] == "NARRE"
+    join = (lambda x: pad_only(x, hp["narre_num_reviews"], hp["narre_num_words"])) if narre else (lambda x: pad_and_join(x, hp["input_length"]))
+    for lo in range(0, len(neg_users), B):
+        acc = [[] for _ in range(7)]
+        for m in range(lo, min(len(neg_users), lo + B)):
+            u, cands = int(neg_users[m]), [int(x) for x in neg_items[m]]
+            i = cands[0]
+            rows = [[] for _ in range(7)]
+            for i2 in cands:
+                u_r, i_r, this, who, what = remove_overlap(user_reviews[u], item_reviews[i2], u_to_i, i_to_u, u, i, None,
+                                                          test_review_of(u, i))
+                who = (who + [hp["total_users"] + 1] * max(0, 10 - len(who)))[:10]
+                what = (what + [hp["total_items"] + 1] * max(0, 10 - len(what)))[:10]
+                for slot, v in zip(rows, (this, who, what, u_r, i_r, u, i2)):
+                    slot.append(v)
+            for slot, v in zip(acc, (join(rows[0]), rows[1], rows[2], join(rows[3]), join(rows[4]), rows[5], rows[6])):
+                slot.append(v)
+        yield acc, [0.0] * len(acc[5])

@@ -262,7 +262,7 @@ class CsrReader:
     NBW = 10                                                            # data.py:277-282
 
     def __init__(self, hyper_params: dict, store: ReviewStore, ratings, train: bool, users=None, items=None,
-                 this_tok=None, this_off=None):
+                 this_tok=None, this_off=None, negs=None):
         self.hp, self.store, self.train = hyper_params, store, bool(train)
         self.bsz = int(hyper_params["batch_size"])
         dev = store.device
@@ -277,6 +277,9 @@ class CsrReader:
             raise ValueError("CsrReader: one rating per (user, item)")
         self.this_tok = to(this_tok, torch.int32) if this_tok is not None else None
         self.this_off = to(this_off, torch.int64) if this_off is not None else None
+        self.negs = None
+        if negs is not None:
+            self._prepare_negs(negs, users, items, this_tok, this_off)
         self.narre = hyper_params["model_type"] == "NARRE"
         self.simple = hyper_params["model_type"] in ("bias_only", "MF", "MF_dot", "NeuMF")      # data.py:33-34 iter_simple
         self.T = int(hyper_params.get("input_length", 1000))
@@ -312,6 +315,70 @@ class CsrReader:
     def iter(self, eval=False):
         for lo in range(0, self.total, self.bsz):
             yield self.batch(lo, min(self.total, lo + self.bsz))
+
+    # ---- ranking candidates (data.py:375-447 iter_negs)
+    def _prepare_negs(self, negs, users, items, this_tok, this_off):
+        """``negs`` = (users [M], items [M, C]) with items[:, 0] the positive item (make_negative_sets.py writes
+        ``negs[user] = [[positive], negatives]``).  The held-out review of (user, positive) is replicated for the C
+        candidates, as the reference hands it to every candidate (data.py:389-397)."""
+        dev = self.store.device
+        nu = np.asarray(negs[0], dtype=np.int64)
+        ni = np.asarray(negs[1], dtype=np.int64).reshape(len(nu), -1)
+        C = ni.shape[1]
+        rows = {}
+        if users is not None and this_off is not None:
+            rows = {(int(u), int(i)): n for n, (u, i) in enumerate(zip(np.asarray(users), np.asarray(items)))}
+        tok_h = np.asarray(this_tok, dtype=np.int32) if this_tok is not None else np.zeros(0, dtype=np.int32)
+        off_h = np.asarray(this_off, dtype=np.int64) if this_off is not None else np.zeros(1, dtype=np.int64)
+        toks, lens = [], []
+        for u, i in zip(nu.tolist(), ni[:, 0].tolist()):
+            n = rows.get((u, i))
+            rev = tok_h[off_h[n]:off_h[n + 1]] if n is not None else np.zeros(1, dtype=np.int32)     # [0] when missing
+            for _ in range(C):
+                toks.append(rev)
+                lens.append(len(rev))
+        to = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(dev)
+        self.negs = {"users": to(nu, torch.int64), "items": to(ni, torch.int64), "C": C,
+                     "this_tok": to(np.concatenate(toks) if toks else np.zeros(0, dtype=np.int32), torch.int32),
+                     "this_off": to(np.concatenate([[0], np.cumsum(lens)]).astype(np.int64), torch.int64)}
+
+    def iter_negs(self, review):
+        if self.negs is None:
+            raise RuntimeError("this reader was built without ranking negatives (negs=...)")
+        st, ng, dev = self.store, self.negs, self.store.device
+        C, M = ng["C"], int(ng["users"].shape[0])
+        for lo in range(0, M, self.bsz):
+            hi = min(M, lo + self.bsz)
+            n = hi - lo
+            items = ng["items"][lo:hi].contiguous()                              # [n, C]
+            users = ng["users"][lo:hi].repeat_interleave(C).view(n, C).contiguous()
+            y = torch.zeros(n, device=dev, dtype=torch.float32)                    # "doesn't matter, only for ranking"
+            if self.simple or not review:
+                yield [None, None, None, None, None, users, items], y
+                continue
+            nc = n * C
+            ids_u, ids_i = users.view(-1), items.view(-1)
+            pos_i = items[:, 0].repeat_interleave(C).contiguous()
+            shape = (nc, self.R, self.W) if self.narre else (nc, self.T)
+            udoc, idoc, this, scratch = (torch.empty(shape, device=dev, dtype=torch.int64) for _ in range(4))
+            items_reviewed = torch.empty(nc, self.NBW, device=dev, dtype=torch.int64)
+            users_who_gave = torch.empty(nc, self.NBW, device=dev, dtype=torch.int64)
+            stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            mode = 1 if self.narre else 0
+            none = _vp(None)
+            # user side: whole document, the items the user reviewed, the held-out review of (user, positive)
+            call("r4r_docs_assemble", _vp(st.tok), _vp(st.rev_off), _vp(st.u_ptr), _vp(st.u_rev), _vp(st.u_nb), st.U, _vp(ids_u), none, nc,
+                 mode, self.T, self.R, self.W, st.I + 1, self.NBW, _vp(udoc), _vp(items_reviewed), _vp(this),
+                 _vp(ng["this_tok"]), _vp(ng["this_off"]), lo * C, stream)
+            # item side: every candidate's own document ...
+            call("r4r_docs_assemble", _vp(st.tok), _vp(st.rev_off), _vp(st.i_ptr), _vp(st.i_rev), _vp(st.i_nb), st.I, _vp(ids_i), none, nc,
+                 mode, self.T, self.R, self.W, st.U + 1, self.NBW, _vp(idoc), none, none, none, none, 0, stream)
+            # ... but the users-who-reviewed list of the POSITIVE item for all of them (remove_overlap(u_r, i_r, u, i))
+            call("r4r_docs_assemble", _vp(st.tok), _vp(st.rev_off), _vp(st.i_ptr), _vp(st.i_rev), _vp(st.i_nb), st.I, _vp(pos_i), none, nc,
+                 mode, self.T, self.R, self.W, st.U + 1, self.NBW, _vp(scratch), _vp(users_who_gave), none, none, none, 0, stream)
+            tail = shape[1:]
+            yield [this.view((n, C) + tail), users_who_gave.view(n, C, self.NBW), items_reviewed.view(n, C, self.NBW),
+                   udoc.view((n, C) + tail), idoc.view((n, C) + tail), users, items], y
 
 
 # ------------------------------------------------------------------------------------------ reference pickles
@@ -349,6 +416,11 @@ def reference_pickles_to_arrays(data_dir: str) -> dict:
     tu, ti, ty = ratings(train)
     out["train_user"], out["train_item"], out["train_y"] = tu, ti, ty
     out["tok"], out["rev_off"] = csr([user_reviews[int(u)][this_index[int(u)][int(i)][0]] for u, i in zip(tu, ti)])
+    import os
+    if os.path.exists(data_dir + "negs.pkl"):                    # data_scripts/make_negative_sets.py: negs[user] = [[positive], negatives]
+        negs = _load_pickle(data_dir + "negs")
+        out["negs_users"] = np.asarray(list(negs), dtype=np.int64)
+        out["negs_items"] = np.asarray([list(negs[u][0]) + list(negs[u][1]) for u in negs], dtype=np.int64).reshape(len(negs), -1)
     for split in ("test", "val"):
         u, i, y = ratings(_load_pickle(data_dir + split))
         held = [test_reviews.get(int(a), {}).get(int(b), [0]) for a, b in zip(u, i)]
@@ -360,12 +432,14 @@ def reference_pickles_to_arrays(data_dir: str) -> dict:
 def load_data(hyper_params: dict, device="cuda"):
     """``data.load_data(hyper_params)`` (data.py:449-482) over device-resident reviews: returns
     ``(train_reader, test_reader, val_reader, hyper_params)`` with ``total_users / total_items / total_words``
-    filled in like the reference (:468-470).  Ranking negatives (``iter_negs``) are not loaded."""
+    filled in like the reference (:468-470).  ``negs.pkl``, when present, gives the test reader ``iter_negs``."""
     a = reference_pickles_to_arrays(hyper_params["data_dir"])
     for k in ("total_users", "total_items", "total_words"):
         hyper_params[k] = a[k]
     store = ReviewStore(a["tok"], a["rev_off"], a["train_user"], a["train_item"], a["total_users"], a["total_items"], device)
     train = CsrReader(hyper_params, store, a["train_y"], train=True)
+    negs = (a["negs_users"], a["negs_items"]) if "negs_users" in a else None
     test, val = (CsrReader(hyper_params, store, a[s + "_y"], train=False, users=a[s + "_user"], items=a[s + "_item"],
-                           this_tok=a[s + "_tok"], this_off=a[s + "_off"]) for s in ("test", "val"))
+                           this_tok=a[s + "_tok"], this_off=a[s + "_off"], negs=negs if s == "test" else None)
+                 for s in ("test", "val"))
     return train, test, val, hyper_params

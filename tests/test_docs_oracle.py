@@ -4,6 +4,7 @@ import os
 
 import numpy as np
 import pytest
+import torch
 
 from tests.helpers import GOLDEN
 
@@ -166,16 +167,61 @@ def test_load_data_wiring_cpu(tmp_path, monkeypatch):
             made["store"] = (tok, rev_off, tu, ti, total_users, total_items, device)
 
     class Reader:
-        def __init__(self, hyper_params, store, ratings, train, users=None, items=None, this_tok=None, this_off=None):
+        def __init__(self, hyper_params, store, ratings, train, users=None, items=None, this_tok=None, this_off=None, negs=None):
             made.setdefault("readers", []).append((train, len(ratings), None if users is None else len(users),
                                                     None if this_off is None else len(this_off)))
+            made.setdefault("negs", []).append(negs)
 
     monkeypatch.setattr(readers, "ReviewStore", Store)
     monkeypatch.setattr(readers, "CsrReader", Reader)
+    import pickle
+    with open(os.path.join(str(tmp_path), "negs.pkl"), "wb") as f:       # make_negative_sets.py format
+        pickle.dump({int(u): [[int(c[0])], [int(x) for x in c[1:]]] for u, c in zip(z["negs.users"], z["negs.items"])}, f, 2)
     hp = dict(hp, data_dir=str(tmp_path) + "/")
     train, test, val, hp2 = readers.load_data(hp, "cuda:0")
+    assert made["negs"][0] is None and made["negs"][2] is None            # only the test reader ranks
+    assert np.array_equal(made["negs"][1][0], z["negs.users"]) and np.array_equal(made["negs"][1][1], z["negs.items"])
     assert hp2 is hp and (hp["total_users"], hp["total_items"], hp["total_words"]) == (U, I, 59)
     tok, rev_off, tu, ti, nu, ni, dev = made["store"]
     assert np.array_equal(tok, z["tok"]) and np.array_equal(rev_off, z["rev_off"]) and (nu, ni, dev) == (U, I, "cuda:0")
     n_eval = len(z["eval_y"])
     assert made["readers"] == [(True, len(z["train_y"]), None, None), (False, 4, 4, 5), (False, n_eval - 4, n_eval - 4, n_eval - 3)]
+
+
+def _held_out(z):
+    revs = split_reviews(z["eval_tok"], z["eval_off"])
+    table = {(int(u), int(i)): r for u, i, r in zip(z["eval_user"], z["eval_item"], revs)}
+    return lambda u, i: table.get((u, i))
+
+
+@pytest.mark.parametrize("mt", ["deepconn", "NARRE"])
+def test_oracle_reproduces_reference_ranking_candidates(mt):
+    from oracle import r4r_data_oracle as D
+    z, hp, (U, I, V) = load_docs_golden(mt)
+    lists = D.review_lists(z["train_user"], z["train_item"], split_reviews(z["tok"], z["rev_off"]), U, I)
+    got = list(D.batches_negs(z["negs.users"], z["negs.items"], lists, hp, _held_out(z)))
+    assert len(got) == int(z["negs.nb"][0])
+    for b, (data, y) in enumerate(got):
+        for j, d in enumerate(data):
+            assert np.array_equal(np.array(d, dtype=np.int64), z["negs.b%d.d%d" % (b, j)]), (b, j)
+        assert np.array_equal(np.array(y, dtype=np.float32), z["negs.b%d.y" % b])
+
+
+def test_ranking_candidates_host_preparation_cpu():
+    """CsrReader._prepare_negs (host): the held-out review of (user, positive item) replicated for the C candidates."""
+    import types
+    from reviews4rec_b200.readers import CsrReader
+    z, hp, (U, I, V) = load_docs_golden("deepconn")
+    store = types.SimpleNamespace(device=torch.device("cpu"))
+    r = CsrReader(hp, store, z["eval_y"], train=False, users=z["eval_user"], items=z["eval_item"],
+                  this_tok=z["eval_tok"], this_off=z["eval_off"], negs=(z["negs.users"], z["negs.items"]))
+    ng, held = r.negs, _held_out(z)
+    assert ng["C"] == 6 and tuple(ng["items"].shape) == (5, 6) and ng["this_off"].numel() == 5 * 6 + 1
+    for m, (u, c) in enumerate(zip(z["negs.users"].tolist(), z["negs.items"].tolist())):
+        want = held(u, c[0])
+        want = [0] if want is None else want
+        for k in range(6):
+            lo, hi = int(ng["this_off"][m * 6 + k]), int(ng["this_off"][m * 6 + k + 1])
+            assert ng["this_tok"][lo:hi].tolist() == list(want)
+    with pytest.raises(RuntimeError):
+        next(CsrReader(hp, store, z["eval_y"], train=False, users=z["eval_user"], items=z["eval_item"]).iter_negs(True))

@@ -97,3 +97,24 @@ def test_neumf_init_fuses_the_pretrained_models():
     for k in want:
         if k != "global_bias":
             assert torch.equal(sd[k].cpu(), want[k]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mt", ["deepconn", "NARRE"])
+def test_device_ranking_candidates_reproduce_reference_iter_negs(mt):
+    """CsrReader.iter_negs == the reference reader's iter_negs (data.py:375-447), golden from the unmodified
+    reference: [bsz, 1+5, ...] inputs incl. the positive item's held-out review / reviewer list for all candidates."""
+    from reviews4rec_b200.readers import CsrReader, ReviewStore
+    z, hp, (U, I, V) = load_docs_golden(mt)
+    store = ReviewStore(z["tok"], z["rev_off"], z["train_user"], z["train_item"], U, I, "cuda")
+    reader = CsrReader(hp, store, z["eval_y"], train=False, users=z["eval_user"], items=z["eval_item"],
+                       this_tok=z["eval_tok"], this_off=z["eval_off"], negs=(z["negs.users"], z["negs.items"]))
+    got = list(reader.iter_negs(True))
+    assert len(got) == int(z["negs.nb"][0])
+    for b, (data, y) in enumerate(got):
+        for j, d in enumerate(data):
+            want = z["negs.b%d.d%d" % (b, j)]
+            assert tuple(d.shape) == tuple(want.shape) and np.array_equal(d.cpu().numpy(), want), (b, j)
+        assert np.array_equal(y.cpu().numpy(), z["negs.b%d.y" % b])
+    simple = list(reader.iter_negs(False))
+    assert simple[0][0][0] is None and np.array_equal(simple[0][0][6].cpu().numpy(), z["negs.b0.d6"])
