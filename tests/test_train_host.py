@@ -73,3 +73,22 @@ def test_main_drivers_control_flow(tmp_path, monkeypatch):
     steps = [e for e in log if e[0] in ("train_complete", "init")]
     assert [s[1] for s in steps] == ["GMF", "MLP", "GMF", "NeuMF"] and steps[2] == ("init", "GMF", "MLP")
     assert steps[0][2].endswith("_gmf") and steps[1][2].endswith("_mlp") and steps[3][2] == hp["model_path"] and steps[3][5] is True
+
+
+def test_config_surface_matches_reference():
+    """reviews4rec_b200.hyper_params against strings produced by the unmodified reference hyper_params.py
+    (tests/golden/common_paths.json, oracle/gen_golden_config.py)."""
+    import json
+    import os
+    from reviews4rec_b200 import hyper_params as H
+    from tests.helpers import GOLDEN
+    g = json.load(open(os.path.join(GOLDEN, "common_paths.json")))
+    assert H.default_hyper_params() == g["defaults"]
+    hp = H.finalize(H.default_hyper_params())
+    assert {k: hp[k] for k in g["default_derived"]} == g["default_derived"]
+    for case in g["cases"]:
+        assert H.get_common_path(case["hyper_params"]) == case["common_path"]
+    hp = H.finalize(dict(H.default_hyper_params(), percent_reviews_to_keep=50))
+    assert hp["data_dir"] == "data/InstantVideo/5_core/50_percent/"
+    narre = dict(H.default_hyper_params(), model_type="NARRE")            # the reference raises KeyError here
+    assert "_only_reviews_False_" in H.get_common_path(narre)
