@@ -5,6 +5,11 @@ from . import ops
 
 
 class MSELoss(torch.nn.Module):
+    """``forward(output, y, return_mean=True)``: per-sample squared error, or its mean.  ``train()`` and
+    ``evaluate()`` call it with ``return_mean=False`` to accumulate the metric (main.py:46,56; eval.py:28,36) and
+    take the mean themselves for the backward pass (main.py:58).  ``hyper_params`` is accepted and ignored, like
+    the reference's constructor."""
+
     def __init__(self, hyper_params=None):
         super().__init__()
 

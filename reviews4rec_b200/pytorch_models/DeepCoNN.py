@@ -9,6 +9,13 @@ from .common_pytorch_models import SmallLinear, TextCNN, TorchFM, WordTable
 
 
 class DeepCoNN(nn.Module):
+    """``deepconn``: FM over the two TextCNN latents + global bias (DeepCoNN.py:64-66); ``deepconn++``: MLP over
+    them + user / item / global biases (:69-72).  All parameters of both heads exist in either mode, exactly like
+    the reference (its state_dict carries ``final.*``, ``fm.*`` and both bias vectors regardless), and the ones the
+    active head does not touch never receive a gradient, so Adam never steps them.  The two word lookups go through
+    ``word2vec.many`` (one exchange when the table is row-sharded) and each tower is a single fused
+    gather + conv + ReLU + max-pool launch followed by the small FC."""
+
     def __init__(self, hyper_params):
         super().__init__()
         self.hyper_params = hyper_params

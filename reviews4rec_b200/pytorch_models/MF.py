@@ -14,6 +14,12 @@ class IdEmbedding(nn.Embedding):
 
 
 class MF(nn.Module):
+    """``bias_only`` / ``MF_dot`` / ``MF`` (MF.py:9-68): biases only; biases + dot product of the (dropped-out) id
+    embeddings; or an MLP over the concatenated embeddings joined with their elementwise product through an FM.
+    Tables have ``total_users + 1`` / ``total_items + 1`` rows (review models: + 2).  Every lookup is
+    ``r4r_rows_gather`` and its backward the dense ``r4r_rows_scatter_add`` gradient that the reference's
+    ``nn.Embedding(sparse=False)`` / ``Tensor.gather`` produce, so Adam updates every row (SURVEY.md finding 5)."""
+
     def __init__(self, hyper_params):
         super().__init__()
         self.hyper_params = hyper_params

@@ -10,6 +10,13 @@ from .MF import IdEmbedding
 
 
 class NARRE(nn.Module):
+    """NARRE (NARRE.py:9-124): every one of the R reviews of a user (item) is its own conv document, the R review
+    features are attended over with the id embedding of the item (user) each review is about, the attended sum is
+    added to the user's (item's) own dropped-out id embedding, and the elementwise product of both sides goes
+    through an MLP plus biases.  Shapes come from the data ([B, R, W] documents, [B, R] neighbour ids), not from
+    ``narre_num_*``.  The neighbour pad ids ``total_users + 1`` / ``total_items + 1`` are hot rows of the id
+    tables: their gradient scatter is combined per warp before the atomics."""
+
     def __init__(self, hyper_params):
         super().__init__()
         self.hyper_params = hyper_params

@@ -10,6 +10,10 @@ from .MF import IdEmbedding
 
 
 class _Biases(nn.Module):
+    """What the three classes share (NeuMF.py:14-16, 43-45, 79-81): user / item bias vectors with
+    ``total_users + 1`` / ``total_items + 1`` entries initialised to 0.1 and a global bias of 4.0, gathered per
+    rating with ``r4r_rows_gather`` (dense gradient scatter in the backward, like ``Tensor.gather``)."""
+
     def __init__(self, hyper_params):
         super().__init__()
         self.hyper_params = hyper_params
@@ -25,6 +29,9 @@ class _Biases(nn.Module):
 
 
 class GMF(_Biases):
+    """Generalised matrix factorisation (NeuMF.py:9-36): a learned linear read-out of the elementwise product of
+    the dropped-out user and item embeddings, plus the biases.  First model of the NeuMF pre-training schedule."""
+
     def __init__(self, hyper_params):
         super().__init__(hyper_params)
         L = hyper_params["latent_size"]
@@ -42,6 +49,9 @@ class GMF(_Biases):
 
 
 class MLP(_Biases):
+    """The MLP half (NeuMF.py:38-73): the concatenated embeddings go through Dropout -> Linear(2L, L) -> ReLU ->
+    Linear(L, L) (``project``, indices 1 and 3 carry the weights) and a linear read-out, plus the biases."""
+
     def __init__(self, hyper_params):
         super().__init__(hyper_params)
         L, p = hyper_params["latent_size"], hyper_params["dropout"]
@@ -61,6 +71,10 @@ class MLP(_Biases):
 
 
 class NeuMF(_Biases):
+    """GMF and MLP side by side with separate embedding tables, read out jointly by ``final`` over the
+    concatenation [gmf product, mlp features] (NeuMF.py:75-138).  ``init`` seeds it from a trained GMF and a
+    trained MLP; ``main.main_NeuMF`` then trains it further with ``train_complete``."""
+
     def __init__(self, hyper_params):
         super().__init__(hyper_params)
         L, p = hyper_params["latent_size"], hyper_params["dropout"]

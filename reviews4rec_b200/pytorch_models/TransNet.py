@@ -10,6 +10,11 @@ from .MF import IdEmbedding
 
 
 class Source(nn.Module):
+    """Source network (TransNet.py:9-37): the user-document and item-document towers, concatenated and projected
+    to the latent space.  Its output is not returned but left on ``self.ir`` -- the train step's transform loss
+    reads it from there (main.py:35-53), and so does ``utils.init_transnet_optim``'s ``optimizer_source`` group.
+    Each tower is one fused gather + conv + pool launch (the ``Docs`` handles carry token ids, not embeddings)."""
+
     def __init__(self, hyper_params):
         super().__init__()
         self.hyper_params = hyper_params
@@ -26,6 +31,10 @@ class Source(nn.Module):
 
 
 class Target(nn.Module):
+    """Target network (TransNet.py:39-61): owns the (frozen) word table shared by all three towers, embeds the
+    review written for this very (user, item) pair and predicts the rating from it with an FM; ``self.ir`` is the
+    representation the source network is trained to reproduce."""
+
     def __init__(self, hyper_params):
         super().__init__()
         self.hyper_params = hyper_params
@@ -36,6 +45,7 @@ class Target(nn.Module):
         self.fm = TorchFM(hyper_params["latent_size"], 8)
 
     def embed(self, review):
+        """Lazy lookup: returns a ``Docs`` handle (ids + table); the rows are gathered inside the conv kernel."""
         return self.word2vec(review)
 
     def forward(self, this):
@@ -44,6 +54,12 @@ class Target(nn.Module):
 
 
 class TransNet(nn.Module):
+    """TransNet / TransNet++ (TransNet.py:63-122).  ``forward`` returns the reference's 3-list
+    ``[source rating [B], target rating [B], mean_b sum_l (source.ir - target.ir)^2]``; the ``++`` variant feeds
+    5-dimensional user / item id embeddings next to ``source.ir`` into ``source_fm``.  Sub-module names, the
+    per-sub-module xavier initialisation at construction (:68-72) and the state_dict layout are the contract
+    ``utils.init_transnet_optim`` (utils.py:70-92) and the checkpoints depend on."""
+
     def __init__(self, hyper_params):
         super().__init__()
         self.hyper_params = hyper_params
