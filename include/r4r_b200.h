@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define R4R_ABI_VERSION 2
+#define R4R_ABI_VERSION 3
 
 #define R4R_EINVAL   (-1)   /* bad argument (null pointer, size out of supported range)          */
 #define R4R_EUNSUP   (-2)   /* shape outside what the sm_100a kernels were built for             */
@@ -103,8 +103,8 @@ int r4r_conv_pool_tc(const void* shadow, int64_t V, int Epad, int E, int dtype,
  * value and max_pool1d keeps the first, so a document whose rows s..T-1 are equal gives bit-identical
  * (pooled, argmax) when cut to doc_len = min(T, s+3) rows, with arg-max positions >= doc_len mapped
  * back by + (T - doc_len).  doc_order = documents by decreasing tile count (load balance).
- * ws: r4r_doc_plan_ws_bytes() bytes of scratch. */
-int64_t r4r_doc_plan_ws_bytes(void);
+ * The order is a stable sort (deterministic: no global atomics).  ws: r4r_doc_plan_ws_bytes(N, T) bytes of scratch. */
+int64_t r4r_doc_plan_ws_bytes(int64_t N, int T);
 int r4r_doc_plan(const int64_t* idx, int64_t N, int T, int32_t* doc_len, int32_t* doc_order, void* ws,
                  void* stream);
 

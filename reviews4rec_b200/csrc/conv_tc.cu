@@ -62,7 +62,10 @@ constexpr int RA = 131;                // rows per A slot: 130 needed (128 + 2 h
                                        // chunk stride RA*16 B maps 8 lanes onto 8 distinct bank groups
 constexpr int N_MAX = 128;             // filters (UMMA N), multiple of 16
 constexpr int ACC_STRIDE = 128;        // TMEM columns between consecutive accumulator buffers
-constexpr int NACC = 4;                // accumulator buffers: the MMA warp may run three tiles ahead of the epilogue,
+#ifndef R4R_NACC
+#define R4R_NACC 4
+#endif
+constexpr int NACC = R4R_NACC;         // accumulator buffers: the MMA warp may run three tiles ahead of the epilogue,
                                        // which hides the per-document reduction (the epilogue drains nothing meanwhile)
 constexpr int TMEM_COLS = NACC * ACC_STRIDE;   // 512 = all of TMEM (1 CTA per SM)
 constexpr int NUM_EPI_WARPS = 8, NUM_PROD_WARPS = 4;
@@ -118,6 +121,10 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t coun
 // st.async + complete_tx.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+// the same with an explicit arrival count (a register operand: lets the caller tie the arrival to earlier loads)
+__device__ __forceinline__ void mbar_arrive_cluster_n(uint32_t cluster_addr, uint32_t count) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0], %1;" :: "r"(cluster_addr), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -397,7 +404,14 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
         const float ov = ctl->xchg_val[b][f];
         const int op = ctl->xchg_pos[b][f];
         if (beats(ov, op, v, p)) { v = ov; p = op; }
-        mbar_arrive_cluster(mapa(smem_u32(&ctl->xchg_empty[b]), 1));
+        // Releasing the buffer lets rank 1 overwrite xchg_*[b] (it may be two documents ahead), so the arrival
+        // must not leave this SM before the two loads above have RETURNED.  A CTA-scope release does not order
+        // this thread's shared-memory loads against another CTA's st.async (the compiler issued the remote
+        // arrive while the loads were still in flight and, with the shared-memory pipe busy feeding the tensor
+        // cores, rank 1's next stores occasionally won the race: round-1 nondeterminism).  A cluster-scope
+        // release would cost MEMBAR.GPU per document; instead the arrival count is made data-dependent on the
+        // merged position, which is computed from both loaded values (always 1: positions are non-negative).
+        mbar_arrive_cluster_n(mapa(smem_u32(&ctl->xchg_empty[b]), 1), 1u + ((uint32_t)p >> 31));
         if (f < P.F) {
           const float o = v + __ldg(P.bias + f);
           P.pooled[doc * P.F + f] = o > 0.0f ? o : 0.0f;

@@ -17,6 +17,7 @@
 //
 // doc_order lists the documents by decreasing tile count so that the persistent CTA pairs, which
 // take work items k = cluster, cluster + nclusters, ... stay in step (longest-processing-time first).
+// The sort is STABLE and free of global atomics: the same batch always yields the same work order.
 #include "common.cuh"
 
 namespace {
@@ -24,8 +25,8 @@ constexpr int THREADS = 256;
 constexpr int NCLASS = 256;              // position tiles per document (conv_tc.cu: <= 256)
 
 // one warp per document: scan backwards for the start of the trailing run of idx[T-1]
-__global__ void __launch_bounds__(THREADS) doc_extent_kernel(const int64_t* __restrict__ idx, int64_t N, int T, int tile,
-                                                             int32_t* __restrict__ doc_len, int32_t* __restrict__ hist) {
+__global__ void __launch_bounds__(THREADS) doc_extent_kernel(const int64_t* __restrict__ idx, int64_t N, int T,
+                                                             int32_t* __restrict__ doc_len) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = (int64_t)gridDim.x * (THREADS / 32);
   for (int64_t n = (int64_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5); n < N; n += warps) {
@@ -45,48 +46,99 @@ __global__ void __launch_bounds__(THREADS) doc_extent_kernel(const int64_t* __re
         if (diff && s == 0) s = hi - 32 * (w + 1) + (32 - __clz(diff));   // one past the highest differing position
       }
     }
-    if (lane == 0) {
-      int len = s + 3 < T ? s + 3 : T;
-      doc_len[n] = len;
-      int c = (len + 2 + tile - 1) / tile;
-      atomicAdd(hist + (c < NCLASS ? c : NCLASS - 1), 1);
-    }
+    if (lane == 0) doc_len[n] = s + 3 < T ? s + 3 : T;
   }
 }
 
 // ragged documents: the trailing padding run starts where the stored tokens end
-__global__ void __launch_bounds__(THREADS) doc_extent_ragged_kernel(const int64_t* __restrict__ offsets, int64_t N, int T, int tile,
-                                                                    int32_t* __restrict__ doc_len, int32_t* __restrict__ hist) {
+__global__ void __launch_bounds__(THREADS) doc_extent_ragged_kernel(const int64_t* __restrict__ offsets, int64_t N, int T,
+                                                                    int32_t* __restrict__ doc_len) {
   for (int64_t n = (int64_t)blockIdx.x * THREADS + threadIdx.x; n < N; n += (int64_t)gridDim.x * THREADS) {
     const int64_t s = __ldg(offsets + n + 1) - __ldg(offsets + n);
     if (s < 0 || s > T) __trap();
-    const int len = s + 3 < T ? (int)s + 3 : T;
-    doc_len[n] = len;
-    const int c = (len + 2 + tile - 1) / tile;
-    atomicAdd(hist + (c < NCLASS ? c : NCLASS - 1), 1);
+    doc_len[n] = s + 3 < T ? (int)s + 3 : T;
   }
 }
 
-// counting sort by tile count, descending; order within a class is arbitrary
-__global__ void __launch_bounds__(THREADS) doc_order_kernel(const int32_t* __restrict__ doc_len, int64_t N, int tile,
-                                                            const int32_t* __restrict__ hist, int32_t* __restrict__ cursor,
-                                                            int32_t* __restrict__ order) {
-  __shared__ int base[NCLASS];
-  for (int c = threadIdx.x; c < NCLASS; c += THREADS) {
-    int b = 0;
-    for (int c2 = c + 1; c2 < NCLASS; ++c2) b += hist[c2];
-    base[c] = b;
-  }
+__device__ __forceinline__ int tile_class(int len, int tile, int ncls) {
+  const int c = (len + 2 + tile - 1) / tile;
+  return c < ncls ? c : ncls - 1;
+}
+
+// Stable counting sort by tile count, descending (documents of one class keep their batch order, so the
+// work order -- and with it every timing-dependent interleaving of the conv kernel -- replays exactly).
+// Pass 1: class histogram of each group of THREADS consecutive documents.
+__global__ void __launch_bounds__(THREADS) doc_group_hist_kernel(const int32_t* __restrict__ doc_len, int64_t N, int tile, int ncls,
+                                                                 int32_t* __restrict__ ghist) {
+  __shared__ int h[NCLASS];
+  h[threadIdx.x] = 0;
   __syncthreads();
-  for (int64_t n = (int64_t)blockIdx.x * THREADS + threadIdx.x; n < N; n += (int64_t)gridDim.x * THREADS) {
-    int c = (doc_len[n] + 2 + tile - 1) / tile;
-    if (c >= NCLASS) c = NCLASS - 1;
-    order[base[c] + atomicAdd(cursor + c, 1)] = (int32_t)n;
+  const int64_t n = (int64_t)blockIdx.x * THREADS + threadIdx.x;
+  if (n < N) atomicAdd(&h[tile_class(doc_len[n], tile, ncls)], 1);      // counts only: order-independent
+  __syncthreads();
+  if ((int)threadIdx.x < ncls) ghist[(int64_t)blockIdx.x * ncls + threadIdx.x] = h[threadIdx.x];
+}
+
+// Pass 2: slot of document n = #documents of longer classes + #documents of its class in earlier groups
+//         + #documents of its class earlier in its own group.
+__global__ void __launch_bounds__(THREADS) doc_order_kernel(const int32_t* __restrict__ doc_len, int64_t N, int tile, int ncls,
+                                                            const int32_t* __restrict__ ghist, int32_t* __restrict__ order) {
+  __shared__ int total[NCLASS], before[NCLASS], base[NCLASS];
+  __shared__ int wcnt[THREADS / 32][NCLASS];
+  const int c0 = threadIdx.x;                         // THREADS == NCLASS: one thread per class
+  if (c0 < ncls) {
+    int t = 0, b = 0;
+    for (int64_t g = 0; g < (int64_t)gridDim.x; ++g) {
+      const int v = ghist[g * ncls + c0];
+      t += v;
+      if (g < (int64_t)blockIdx.x) b += v;
+    }
+    total[c0] = t;
+    before[c0] = b;
+  }
+  for (int w = 0; w < THREADS / 32; ++w) wcnt[w][c0] = 0;
+  __syncthreads();
+  if (c0 < ncls) {
+    int b = before[c0];
+    for (int c2 = c0 + 1; c2 < ncls; ++c2) b += total[c2];
+    base[c0] = b;
+  }
+  const int64_t n = (int64_t)blockIdx.x * THREADS + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = n < N ? tile_class(doc_len[n], tile, ncls) : -1;
+  const unsigned same = __match_any_sync(0xffffffffu, c);
+  const int rank_in_warp = __popc(same & ((1u << lane) - 1u));
+  if (c >= 0 && rank_in_warp == 0) wcnt[warp][c] = __popc(same);
+  __syncthreads();
+  if (c >= 0) {
+    int slot = base[c] + rank_in_warp;
+    for (int w = 0; w < warp; ++w) slot += wcnt[w][c];
+    order[slot] = (int32_t)n;
   }
 }
 }  // namespace
 
-extern "C" int64_t r4r_doc_plan_ws_bytes(void) { return 2 * NCLASS * (int64_t)sizeof(int32_t); }
+static int plan_classes(int T, int tile) {
+  int c = (T + 2 + tile - 1) / tile + 1;
+  return c < NCLASS ? c : NCLASS;
+}
+
+extern "C" int64_t r4r_doc_plan_ws_bytes(int64_t N, int T) {
+  if (N < 0 || T <= 0) return -1;
+  return (cdiv64(N, THREADS) * plan_classes(T, 256) + 1) * (int64_t)sizeof(int32_t);
+}
+
+static int doc_order_launch(int64_t N, int T, const int32_t* doc_len, int32_t* doc_order, void* ws, cudaStream_t s) {
+  const int tile = 256;                               // positions per CTA-pair tile of conv_pool_tc (2 * TILE_M)
+  const int ncls = plan_classes(T, tile);
+  const unsigned groups = (unsigned)cdiv64(N, THREADS);
+  int32_t* ghist = static_cast<int32_t*>(ws);
+  doc_group_hist_kernel<<<groups, THREADS, 0, s>>>(doc_len, N, tile, ncls, ghist);
+  R4R_CHECK_LAUNCH("doc_group_hist");
+  doc_order_kernel<<<groups, THREADS, 0, s>>>(doc_len, N, tile, ncls, ghist, doc_order);
+  R4R_CHECK_LAUNCH("doc_order");
+  return 0;
+}
 
 extern "C" int r4r_doc_plan(const int64_t* idx, int64_t N, int T, int32_t* doc_len, int32_t* doc_order, void* ws,
                             void* stream) {
@@ -94,19 +146,11 @@ extern "C" int r4r_doc_plan(const int64_t* idx, int64_t N, int T, int32_t* doc_l
   R4R_REQUIRE(N >= 0 && N < (1LL << 31) && T > 0, R4R_EINVAL, "doc_plan: bad sizes");
   if (N == 0) return 0;
   cudaStream_t s = as_stream(stream);
-  const int tile = 256;                               // positions per CTA-pair tile of conv_pool_tc (2 * TILE_M)
-  int32_t* hist = static_cast<int32_t*>(ws);
-  int32_t* cursor = hist + NCLASS;
-  R4R_CUDA(cudaMemsetAsync(ws, 0, (size_t)r4r_doc_plan_ws_bytes(), s));
   int64_t b = cdiv64(N, THREADS / 32);
   if (b > 148 * 8) b = 148 * 8;
-  doc_extent_kernel<<<(unsigned)b, THREADS, 0, s>>>(idx, N, T, tile, doc_len, hist);
+  doc_extent_kernel<<<(unsigned)b, THREADS, 0, s>>>(idx, N, T, doc_len);
   R4R_CHECK_LAUNCH("doc_extent");
-  b = cdiv64(N, THREADS);
-  if (b > 148) b = 148;
-  doc_order_kernel<<<(unsigned)b, THREADS, 0, s>>>(doc_len, N, tile, hist, cursor, doc_order);
-  R4R_CHECK_LAUNCH("doc_order");
-  return 0;
+  return doc_order_launch(N, T, doc_len, doc_order, ws, s);
 }
 
 extern "C" int r4r_doc_plan_ragged(const int64_t* offsets, int64_t N, int T, int32_t* doc_len, int32_t* doc_order, void* ws,
@@ -115,15 +159,9 @@ extern "C" int r4r_doc_plan_ragged(const int64_t* offsets, int64_t N, int T, int
   R4R_REQUIRE(N >= 0 && N < (1LL << 31) && T > 0, R4R_EINVAL, "doc_plan_ragged: bad sizes");
   if (N == 0) return 0;
   cudaStream_t s = as_stream(stream);
-  const int tile = 256;
-  int32_t* hist = static_cast<int32_t*>(ws);
-  int32_t* cursor = hist + NCLASS;
-  R4R_CUDA(cudaMemsetAsync(ws, 0, (size_t)r4r_doc_plan_ws_bytes(), s));
   int64_t b = cdiv64(N, THREADS);
   if (b > 148) b = 148;
-  doc_extent_ragged_kernel<<<(unsigned)b, THREADS, 0, s>>>(offsets, N, T, tile, doc_len, hist);
+  doc_extent_ragged_kernel<<<(unsigned)b, THREADS, 0, s>>>(offsets, N, T, doc_len);
   R4R_CHECK_LAUNCH("doc_extent_ragged");
-  doc_order_kernel<<<(unsigned)b, THREADS, 0, s>>>(doc_len, N, tile, hist, cursor, doc_order);
-  R4R_CHECK_LAUNCH("doc_order");
-  return 0;
+  return doc_order_launch(N, T, doc_len, doc_order, ws, s);
 }

@@ -30,8 +30,9 @@ def evaluate(model, criterion, reader, hyper_params, user_count, item_count, rev
             else:
                 se = criterion(output, y, return_mean=False)
             se_parts.append(se.reshape(-1))
-            user_parts.append(data[5].reshape(-1))
-            item_parts.append(data[6].reshape(-1))
+            # copies: a reader may hand out views of staging buffers it reuses (RaggedReader's two slots)
+            user_parts.append(data[5].reshape(-1).clone())
+            item_parts.append(data[6].reshape(-1).clone())
             total_batches += 1.0
         if not se_parts:
             return {}, {}, {}

@@ -38,7 +38,7 @@ def model_class(model_type):
 def _final_metrics(hyper_params, model, test_reader, user_count, item_count, review, start_time):
     criterion = MSELoss(hyper_params)
     metrics, user_map, item_map = evaluate(model, criterion, test_reader, hyper_params, user_count, item_count, review=review)
-    if hasattr(test_reader, "iter_negs"):                       # HR@1 needs the sampled negatives (data.py:375-447)
+    if getattr(test_reader, "negs", None) is not None:          # HR@1 needs the sampled negatives (data.py:375-447)
         metrics.update(eval_ranking(model, test_reader, hyper_params, review=review))
     log_end_epoch(hyper_params, metrics, "final", time.time() - start_time, metrics_on="(TEST)")
     return metrics, user_map, item_map

@@ -52,7 +52,7 @@ def doc_lengths(idx: "torch.Tensor") -> "torch.Tensor":
         (N, T), dev = idx.shape, idx.device
     doc_len = torch.empty(N, device=dev, dtype=torch.int32)
     order = torch.empty(N, device=dev, dtype=torch.int32)
-    ws = torch.empty(_lib.lib.r4r_doc_plan_ws_bytes(), device=dev, dtype=torch.uint8)
+    ws = torch.empty(_lib.lib.r4r_doc_plan_ws_bytes(N, T), device=dev, dtype=torch.uint8)
     if N and rg is None:
         call("r4r_doc_plan", _p(idx), N, T, _p(doc_len), _p(order), _p(ws), _stream())
     elif N:
@@ -301,6 +301,11 @@ def conv_pool_forward(idx: torch.Tensor, table: torch.Tensor, conv_w: torch.Tens
     pooled = torch.empty(N, F, device=dev, dtype=torch.float32)
     argmax = torch.empty(N, F, device=dev, dtype=torch.int32)
     used = None
+    if N == 0:                                                   # empty batch: nothing to launch
+        if mode != "exact":
+            shadow = shadow if shadow is not None else ShadowTable()
+            used = (shadow.get(table, mode), shadow.epad, V)
+        return (pooled, argmax, used) if want_shadow else (pooled, argmax)
     if mode == "exact":
         keys = torch.empty(N, F, device=dev, dtype=torch.int64)
         with _ConvTimer():
@@ -321,7 +326,7 @@ def conv_pool_forward(idx: torch.Tensor, table: torch.Tensor, conv_w: torch.Tens
             # r4r_doc_plan in include/r4r_b200.h) and issued longest first
             doc_len = torch.empty(N, device=dev, dtype=torch.int32)
             doc_order = torch.empty(N, device=dev, dtype=torch.int32)
-            ws = torch.empty(_lib.lib.r4r_doc_plan_ws_bytes(), device=dev, dtype=torch.uint8)
+            ws = torch.empty(_lib.lib.r4r_doc_plan_ws_bytes(N, T), device=dev, dtype=torch.uint8)
             if ragged is None:
                 call("r4r_doc_plan", _p(idx), N, T, _p(doc_len), _p(doc_order), _p(ws), _stream())
             else:
@@ -364,6 +369,8 @@ class _ConvPool(torch.autograd.Function):
         N, T = (int(rg.shape[0]), int(rg.shape[1])) if rg is not None else idx.shape
         dW = zeros_f32(ctx.wshape, pooled.device)
         db = zeros_f32((F,), pooled.device)
+        if N == 0:                                               # empty batch: zero gradients, nothing to launch
+            return None, (torch.zeros_like(table) if ctx.table_grad else None), dW, db, None, None
         if ctx.used is None:
             call("r4r_conv_wgrad_argmax", _p(table), table.shape[0], E, _p(idx), N, T, _p(argmax), _p(pooled),
                  _p(_f32c(gpooled)), F, _p(dW), _p(db), _stream())

@@ -56,7 +56,6 @@ class TextCNN(nn.Module):
             for w in window_sizes])
         self.fc = nn.Linear(self.num_filters * len(window_sizes), hyper_params["latent_size"])
         self.dropout = nn.Dropout(hyper_params["dropout"])
-        self._dense_shadow = ops.ShadowTable()
 
     def pooled(self, x):
         """[N,100] relu+max-pooled conv features of ``x`` (a Docs handle or a dense [N,T,E] tensor)."""
@@ -68,7 +67,9 @@ class TextCNN(nn.Module):
                                "a trainable word table goes through the WordTable / Docs handle")
         n, t, e = x.shape                                   # reference signature: embedded docs [N,T,E]
         idx = torch.arange(n * t, device=x.device, dtype=torch.int64).view(n, t)
-        return ops.conv_pool(idx, x.reshape(n * t, e), conv.weight, conv.bias, shadow=self._dense_shadow)
+        # a fresh shadow per call: activations are not a frozen table (the caching allocator hands a new tensor
+        # the old address and version, which is exactly ShadowTable's cache key)
+        return ops.conv_pool(idx, x.reshape(n * t, e), conv.weight, conv.bias, shadow=ops.ShadowTable())
 
     def forward(self, x):
         return self.dropout(ops.linear(self.pooled(x), self.fc.weight, self.fc.bias))

@@ -283,7 +283,7 @@ class CsrReader:
         self.narre = hyper_params["model_type"] == "NARRE"
         self.simple = hyper_params["model_type"] in ("bias_only", "MF", "MF_dot", "NeuMF")      # data.py:33-34 iter_simple
         self.T = int(hyper_params.get("input_length", 1000))
-        self.R, self.W = int(hyper_params.get("narre_num_reviews", 10)), int(hyper_params.get("narre_num_words", 200))
+        self.R, self.W = int(hyper_params.get("narre_num_reviews", 10)), int(hyper_params.get("narre_num_words", 100))
 
     def __len__(self):
         return self.total // self.bsz + int(self.total % self.bsz > 0)

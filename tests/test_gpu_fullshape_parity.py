@@ -1,0 +1,240 @@
+"""Parity against the oracle AT THE BENCHMARKED SHAPE in the benchmarked modes (BASELINE.json configs[1]:
+DeepCoNN, E=300, F=100, T=1000, L=10, V=50,001, U=1M, I=100k; the synthetic Amazon-shaped batches bench.py trains on).
+
+  * 120 Adam steps of 64 ratings on both sides from the same initial parameters: train-loop MSE to 1e-4 relative over the first 30 steps and 3e-4
+    over all 120 (main.py:55-66; north_star; bf16 operands: 5e-4 / 1e-3);
+  * at three points of the ORACLE's trajectory (steps 0, 40 and 120: conv filters grow ~10x, SURVEY.md section 7
+    "Precision vs 1e-4" asks for a re-check once the features have grown) the oracle's parameters are loaded into the
+    device model and 256 held-out ratings are compared: pooled conv features [N,100] of both towers, latent vectors,
+    ratings (1e-4 relative AND relative to the spread of the ratings, because global_bias = 4.0 dominates their
+    magnitude), sum of squared errors, and every parameter's gradient on a further batch;
+  * the reference's own long-document golden (tests/golden/deepconn_long.npz: T=700, padding runs of every length,
+    three position tiles per document) through the multi-tile path and the padding-run work plan.
+
+Why the parameters are re-synchronised instead of comparing the two 120-step trajectories: this training loop is
+chaotic.  Adam's update lr * m / (sqrt(v) + eps) is ~ lr * sign(g) wherever |g| >> eps = 1e-8, and the conv gradient
+flows only through each filter's arg-max window, so a last-bit difference flips an arg-max or a near-zero gradient's
+sign and the filters drift apart at ~lr per step.  The reference's own arithmetic shows it (measured in the build
+container with the oracle, same inputs, same code):
+  fp32 vs fp64            pooled features agree to 2e-7 after 20 steps, differ by 1.4e-3 after 40, 2.9e-2 after 60 and
+                          3.9e-2 after 120 (largest feature 0.13); ratings then differ by 5e-3 = their whole spread
+  fp32, 8 vs 1 CPU thread cumulative train-loop MSE deviates by 2e-6 after 20 steps, 8.9e-5 after 60, 4.5e-5 after 120
+  fp32 vs fp64            cumulative train-loop MSE: <= 3e-8 up to 40 steps, 2.9e-5 after 120
+So bit-level trajectory parity beyond ~30 steps is not a property the reference has with itself, and its own 120-step
+MSE is reproducible to ~1e-4 only.  The tests therefore demand 1e-4 on the first 30 steps (before the trajectories
+separate), 3e-4 on all 120, and per-state parity along the oracle's trajectory.
+
+Fast modes (f16 / bf16 conv operands) are compared twice: with the fp32 oracle (what the rounding of the operands costs:
+features, ratings) and with the oracle evaluated ON THE ROUNDED OPERANDS (word table and conv filters rounded to the
+mode's type, everything in fp32), which the kernels must reproduce tightly -- including every parameter gradient.  The
+gradient is not compared element-wise with the fp32 oracle: rounding moves ~0.4 % of the (document, filter) arg-max
+positions to another near-tied window, and each such move re-routes that document's whole contribution to dW[f]
+(measured: 12 % of the largest entry), exactly as cuDNN's TF32 convolution would on the reference's own GPU path.
+
+The oracle runs on the host cores in ~25 s at these sizes."""
+import os
+import pickle
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import assert_close, golden_batches, golden_state, load_golden
+
+pytestmark = pytest.mark.gpu
+
+V, B, STEPS, HELD = 50001, 64, 120, 4
+HP = {"model_type": "deepconn", "latent_size": 10, "word_embed_size": 300, "dropout": 0.0, "total_users": 1_000_000,
+      "total_items": 100_000, "lr": 0.002, "weight_decay": 1e-6, "input_length": 1000, "batch_size": B}
+# conv operand precision -> tolerance on pooled features / latent vectors, relative to the largest magnitude
+# (f16: 11-bit significands, bf16: 8-bit; fp32 accumulation in both)
+FEATURE_TOL = {"exact": 2e-5, "f16": 3e-4, "bf16": 2.4e-3}
+
+
+def _cat(batches):
+    data = [None if batches[0][0][j] is None else torch.cat([b[0][j] for b in batches]) for j in range(7)]
+    return data, torch.cat([b[1] for b in batches])
+
+
+SNAPSHOTS = (0, 30, 120)
+ROUND = {"f16": torch.float16, "bf16": torch.bfloat16}
+ROUNDED_KEYS = ("word2vec.weight", "user_conv.convs.0.weight", "item_conv.convs.0.weight")
+
+
+@pytest.fixture(scope="module")
+def world():
+    from oracle import r4r_oracle as O
+    from reviews4rec_b200.synthetic import SyntheticReader
+    hp = dict(HP)
+    P0 = O.init_params(hp, V, seed=5)
+    batches = SyntheticReader(hp, B, HELD + 1 + STEPS, V, seed=1234).batches
+    held, probe, train = _cat(batches[:HELD]), batches[HELD], batches[HELD + 1:]
+
+    def state(P, rounded=True):
+        f = {"P": {k: v.clone() for k, v in P.items()}}
+        if rounded:                                             # the same state seen through the fast modes' operand rounding
+            for m, dt in ROUND.items():
+                f[m] = state({k: (v.to(dt).float() if k in ROUNDED_KEYS else v) for k, v in P.items()}, rounded=False)
+        with torch.no_grad():
+            for side, j in (("user", 3), ("item", 4)):
+                x = O.word_gather(P["word2vec.weight"], held[0][j])
+                f["pooled." + side], _ = O.conv_pool(x, P[side + "_conv.convs.0.weight"], P[side + "_conv.convs.0.bias"])
+                f["latent." + side] = O.text_cnn(P, side + "_conv.", x, 0.0, False)
+            f["rating"] = O.forward(P, held[0], hp, train=False)
+            f["se_sum"] = float(O.mse(f["rating"], held[1], return_mean=False).double().sum())
+        f["grads"] = O.grads_of(P, probe[0], probe[1], hp, train=True)[2]
+        return f
+
+    P = {k: v.clone() for k, v in P0.items()}
+    states, opt, tot, n, done, mse = {0: state(P)}, None, 0.0, 0, 0, {}
+    for upto in SNAPSHOTS[1:]:
+        _, t, k, opt = O.train_batches(P, train[done:upto], hp, opt=opt)
+        tot, n, done = tot + t, n + k, upto
+        mse[upto] = tot / n
+        states[upto] = state(P)
+    tmp = tempfile.mkdtemp()
+    with open(os.path.join(tmp, "word2vec.pkl"), "wb") as f:
+        pickle.dump(np.zeros((V, HP["word_embed_size"]), dtype=np.float32), f, 2)
+    hp["data_dir"] = tmp
+    return dict(hp=hp, P0=P0, held=held, probe=probe, train=train, states=states, mse=mse)
+
+
+def _device_features(model, held):
+    data = [None if d is None else d.cuda() for d in held[0]]
+    f = {}
+    model.eval()
+    with torch.no_grad():
+        for side, j, tower in (("user", 3, model.user_conv), ("item", 4, model.item_conv)):
+            f["pooled." + side] = tower.pooled(model.word2vec(data[j]))
+            f["latent." + side] = tower(model.word2vec(data[j]))
+        f["rating"] = model(data)
+        f["se_sum"] = float(((f["rating"] - held[1].cuda()) ** 2).double().sum())
+    return f
+
+
+# ratings are ~4.2 +- 0.007 even after training (the reference xavier-initialises the word table, SURVEY.md finding 2,
+# so conv features stay small next to global_bias): 1e-4 relative alone would be a weak check, hence the error is
+# ALSO bounded relative to the spread of the ratings around their mean (the part the towers actually contribute)
+SPREAD_TOL = {"exact": 1e-3, "f16": 2e-2, "bf16": 1e-1}
+REPORT = {}
+
+
+def _check(got, ref, mode, what, tol_as=None):
+    rep = REPORT.setdefault(mode, {}).setdefault(what, {})
+    tol_as = tol_as or mode
+    for k in ("pooled.user", "pooled.item", "latent.user", "latent.item"):
+        scale = float(ref[k].abs().max())
+        err = float((got[k].cpu() - ref[k]).abs().max())
+        rep[k] = {"max_abs_err": err, "max_abs_ref": scale}
+        assert err <= FEATURE_TOL[tol_as] * scale, "%s %s [%s]: max |err| %.3e vs %.3e * %.3e" % (what, k, mode, err, FEATURE_TOL[mode], scale)
+    r, g = ref["rating"].double(), got["rating"].cpu().double()
+    spread = float(r.std())
+    rep["rating"] = {"max_rel_err": float(((g - r).abs() / r.abs()).max()), "max_abs_err": float((g - r).abs().max()),
+                     "std_of_reference_ratings": spread, "se_sum": got["se_sum"], "se_sum_ref": ref["se_sum"]}
+    assert_close(got["rating"], ref["rating"], rtol=1e-4, atol=0.0, msg="%s ratings [%s]" % (what, mode))
+    assert float((g - r).abs().max()) <= SPREAD_TOL[tol_as] * spread, "%s ratings [%s]: max |err| %.3e vs spread %.3e" % (
+        what, mode, float((g - r).abs().max()), spread)
+    assert abs(got["se_sum"] - ref["se_sum"]) <= 1e-4 * ref["se_sum"], (what, mode, got["se_sum"], ref["se_sum"])
+
+
+def _save_report():
+    import json
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "fullshape_parity.json"), "w") as f:
+            json.dump(REPORT, f, indent=1, sort_keys=True)
+
+
+GRAD_TOL = 1e-4          # per tensor, relative to its largest gradient entry (fast modes: vs the oracle on rounded operands)
+
+
+@pytest.mark.parametrize("mode", ["exact", "f16", "bf16"])
+def test_benchmarked_shape_120_adam_steps_and_parity_along_the_trajectory(world, mode):
+    import reviews4rec_b200 as R
+    from reviews4rec_b200 import ops
+    from reviews4rec_b200.optim import FusedAdam
+    from reviews4rec_b200.train import train
+    from tests.test_gpu_models import ListReader
+    ops.set_conv_mode(mode)
+    try:
+        hp = world["hp"]
+        model = R.DeepCoNN(hp)
+        model.load_state_dict(world["P0"])
+        model = model.cuda()
+        # ---- (1) the device's own 120-step training run: train-loop MSE after 30 steps (1e-4) and after all 120 (3e-4)
+        opt = FusedAdam(model.parameters(), lr=HP["lr"], weight_decay=HP["weight_decay"])
+        dev_batches = [([None if d is None else d.cuda() for d in data], y.cuda()) for data, y in world["train"]]
+        tot = n = done = 0
+        # bf16 (8-bit significands) is the one mode whose operand rounding shows in the loop MSE: measured 1.7e-4 / 3e-4
+        for upto, tol in zip(SNAPSHOTS[1:], (5e-4, 1e-3) if mode == "bf16" else (1e-4, 3e-4)):
+            train(model, R.MSELoss(hp), opt, ListReader(dev_batches[done:upto]), hp)
+            tot, n, done = tot + train.last_raw["se_sum"], n + train.last_raw["n"], upto
+            mse, ref = tot / n, world["mse"][upto]
+            REPORT.setdefault(mode, {})["train_loop_%d_steps" % upto] = {"mse": mse, "mse_oracle": ref, "rel_dev": abs(mse / ref - 1.0), "batch": B}
+            assert n == upto * B
+            assert abs(mse - ref) <= tol * ref, "train-loop MSE after %d steps [%s]: %.7f vs oracle %.7f" % (upto, mode, mse, ref)
+        # ---- (2) parity at points of the oracle's trajectory (parameters re-synchronised, see the module docstring)
+        pdata = [None if d is None else d.cuda() for d in world["probe"][0]]
+        py = world["probe"][1].cuda()
+        for step in SNAPSHOTS:
+            st = world["states"][step]
+            model.load_state_dict(st["P"])
+            what = "oracle parameters after %d steps" % step
+            feats = _device_features(model, world["held"])
+            _check(feats, st, mode, what + " (vs fp32 oracle)")
+            tight = st if mode == "exact" else st[mode]          # the oracle on this mode's rounded operands
+            if mode != "exact":
+                _check(feats, tight, mode, what + " (vs oracle on rounded operands)", tol_as="exact")
+            model.train()
+            model.zero_grad()
+            R.MSELoss(hp)(model(pdata), py).backward()
+            rep = REPORT[mode][what + " (vs fp32 oracle)"].setdefault("grads_vs_oracle_on_rounded_operands" if mode != "exact" else "grads", {})
+            for k, p in model.named_parameters():
+                ref = tight["grads"].get(k)
+                if ref is None:
+                    assert p.grad is None, k
+                    continue
+                scale, err = float(ref.abs().max()), float((p.grad.cpu() - ref).abs().max())
+                rep[k] = {"max_abs_err": err, "max_abs_ref": scale}
+                assert err <= GRAD_TOL * scale + 1e-9, "%s grad %s [%s]: max |err| %.3e vs max |g| %.3e" % (what, k, mode, err, scale)
+    finally:
+        ops.set_conv_mode("f16")
+        _save_report()
+
+
+@pytest.mark.parametrize("mode", ["exact", "f16", "bf16"])
+def test_reference_long_document_golden(mode):
+    """Pinned to the unmodified reference (oracle/gen_golden_long.py): T=700 -> three position tiles, work plan on."""
+    import reviews4rec_b200 as R
+    from reviews4rec_b200.optim import FusedAdam
+    from reviews4rec_b200.train import train
+    from tests.test_gpu_models import ListReader, build
+    z, dims = load_golden("deepconn_long")
+    model, hp = build("deepconn", z, dims, mode=mode)
+    data, y = golden_batches(z, dims, "cuda")[0]
+    model.eval()
+    with torch.no_grad():
+        for side, j, tower in (("user", 3, model.user_conv), ("item", 4, model.item_conv)):
+            ref = torch.from_numpy(z["pooled." + side])
+            err = float((tower.pooled(model.word2vec(data[j])).cpu() - ref).abs().max())
+            assert err <= FEATURE_TOL[mode] * float(ref.abs().max()), (side, mode, err)
+        # O(1) word vectors here (unlike the reference's xavier-initialised table): the operand rounding of the fast
+        # modes shows in the ratings -- f16 ~1e-4 relative, bf16 (8-bit significands) ~8x that
+        assert_close(model(data), z["eval.out0"], rtol=1e-4, atol={"exact": 1e-5, "f16": 4e-4, "bf16": 3e-3}[mode], msg="eval.out0")
+    model.train()
+    if mode == "exact":
+        out = model(data)
+        R.MSELoss(hp)(out, y).backward()
+        for k in [k[5:] for k in z.files if k.startswith("grad.")]:
+            assert_close(dict(model.named_parameters())[k].grad, z["grad." + k], rtol=1e-4, atol=1e-6, msg="grad." + k)
+        model.zero_grad()
+    opt = FusedAdam(model.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"])
+    metrics = train(model, R.MSELoss(hp), opt, ListReader(golden_batches(z, dims, "cuda")), hp)
+    tol = {"exact": 1e-4, "f16": 5e-4, "bf16": 4e-3}[mode]
+    assert abs(metrics["MSE"] - float(z["metric.MSE"])) <= tol * max(1.0, float(z["metric.MSE"])) + 5e-5, (mode, metrics["MSE"])
+    if mode == "exact":
+        ref = golden_state(z, "final")
+        sd = model.state_dict()
+        for k in ref:
+            assert_close(sd[k], ref[k], rtol=1e-4, atol=4e-6, msg="final." + k)

@@ -154,17 +154,17 @@ def _ragged_docs(seed, N, T, V):
     return idx
 
 
-@pytest.mark.parametrize("N,T", [(40, 1000), (25, 600), (12, 257), (9, 300)])
+@pytest.mark.parametrize("N,T", [(40, 1000), (25, 600), (12, 257), (9, 300), (1000, 1000)])
 def test_doc_plan_kernel(R, N, T):
-    """r4r_doc_plan: doc_len = min(T, start of the trailing run + 3); doc_order = permutation by
-    decreasing CTA-pair tile count."""
+    """r4r_doc_plan: doc_len = min(T, start of the trailing run + 3); doc_order = the STABLE permutation by
+    decreasing CTA-pair tile count (documents of one class keep their batch order: no atomics, replays exactly)."""
     import ctypes
     from reviews4rec_b200 import _lib
     idx = _ragged_docs(5, N, T, 50)
     d = idx.cuda()
     doc_len = torch.empty(N, dtype=torch.int32, device="cuda")
     order = torch.empty(N, dtype=torch.int32, device="cuda")
-    ws = torch.empty(_lib.lib.r4r_doc_plan_ws_bytes(), dtype=torch.uint8, device="cuda")
+    ws = torch.empty(_lib.lib.r4r_doc_plan_ws_bytes(N, T), dtype=torch.uint8, device="cuda")
     vp = lambda t: ctypes.c_void_p(t.data_ptr())
     _lib.call("r4r_doc_plan", vp(d), N, T, vp(doc_len), vp(order), vp(ws), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     want = []
@@ -179,6 +179,7 @@ def test_doc_plan_kernel(R, N, T):
     assert sorted(o) == list(range(N))
     tiles = [(want[n] + 2 + 255) // 256 for n in o]
     assert tiles == sorted(tiles, reverse=True)
+    assert o == sorted(range(N), key=lambda n: -((want[n] + 2 + 255) // 256))      # python's sort is stable
 
 
 @pytest.mark.parametrize("mode", ["f16", "bf16"])
@@ -322,3 +323,19 @@ def test_fused_adam_matches_torch(R):
         assert_close(a, b, rtol=1e-6, atol=1e-7, msg="param %s" % (s,))
     # untouched rows of the big table still move (weight decay + bias-corrected moments): finding 5
     assert float((mine[0][5000:] - ps[0].cuda()[5000:]).abs().max()) > 0
+
+
+@pytest.mark.parametrize("mode", ["exact", "f16"])
+def test_conv_pool_empty_batch(R, mode):
+    """Zero documents (an empty trailing batch): empty outputs, no launch, zero weight gradients."""
+    from reviews4rec_b200 import ops
+    g = gen(5)
+    table = torch.randn(30, 16, generator=g).cuda()
+    w = torch.randn(100, 1, 3, 16, generator=g).cuda().requires_grad_(True)
+    b = torch.randn(100, generator=g).cuda().requires_grad_(True)
+    idx = torch.zeros(0, 300, dtype=torch.int64, device="cuda")
+    p, a = ops.conv_pool_forward(idx, table, w.detach(), b.detach(), mode)
+    assert tuple(p.shape) == (0, 100) and tuple(a.shape) == (0, 100)
+    out = ops.conv_pool(idx, table, w, b, mode=mode)
+    out.sum().backward()
+    assert float(w.grad.abs().max()) == 0.0 and float(b.grad.abs().max()) == 0.0

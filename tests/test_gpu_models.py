@@ -221,3 +221,27 @@ def test_captured_step_equals_eager_training(mt):
         # same tolerances as the reference train-loop test: atomics make the gradient summation order vary
         atol = hp["lr"] * 3 * dims["NB"] if (mt == "NARRE" and k.startswith("attention_scorer_") and k.endswith(".3.bias")) else 4e-6
         assert_close(b[k], a[k], rtol=1e-4, atol=atol, msg="%s %s" % (mt, k))
+
+
+@pytest.mark.parametrize("mode", ["exact", "f16"])
+def test_textcnn_dense_input_twice_with_different_activations(mode):
+    """TextCNN(x) with the reference's dense [N,T,E] input (common_pytorch_models.py:22-39).  Two calls with
+    different activations of the same shape: the half-precision operand copy must be rebuilt each time (the caching
+    allocator re-uses addresses, so a cached copy keyed on the pointer would silently serve the first call's rows)."""
+    import torch.nn.functional as Fn
+    from reviews4rec_b200 import ops
+    from reviews4rec_b200.pytorch_models.common_pytorch_models import TextCNN
+    ops.set_conv_mode(mode)
+    g = torch.Generator().manual_seed(11)
+    hp = {"word_embed_size": 24, "latent_size": 6, "dropout": 0.0}
+    m = TextCNN(hp).cuda().eval()
+    conv, fc = m.convs[0], m.fc
+    tol = dict(rtol=1e-4, atol=1e-5) if mode == "exact" else dict(rtol=3e-3, atol=3e-3)
+    for trial in range(3):
+        x = torch.randn(7, 40, 24, generator=g).cuda()
+        with torch.no_grad():
+            got = m(x)
+            ref = Fn.conv2d(x.unsqueeze(1), conv.weight, conv.bias, padding=(2, 0)).relu().squeeze(3)
+            ref = Fn.linear(Fn.max_pool1d(ref, ref.shape[2]).squeeze(2), fc.weight, fc.bias)
+        torch.testing.assert_close(got, ref, **tol)
+        del x, got, ref

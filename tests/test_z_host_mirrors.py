@@ -1,22 +1,16 @@
 """Host-side mirrors of the reference's driver functions, exercised end to end on the GPU:
-``readers.load_data`` (data.py:449-482) and ``train.train_complete`` (main.py:73-136).  The file sorts last on
-purpose: these two tests were written after the round's GPU budget was spent and have not run on a GPU yet, so
-under ``pytest -x`` they cannot mask the verified suite."""
+``readers.load_data`` (data.py:449-482), ``train.train_complete`` (main.py:73-136), the GMF / MLP / NeuMF classes
+and the ranking-candidate reader."""
 import numpy as np
 import pytest
 import torch
 
 from tests.helpers import golden_batches, load_golden
 
-# Not one of these tests has run on a GPU yet (the round's GPU budget was spent before they were written; their
-# host logic and oracles are CPU-tested).  Non-strict xfail: an unexpected failure is reported as XFAIL instead of
-# turning the verified suite red, a pass is reported as XPASS.  Remove the marker after the first green GPU run.
-unverified = pytest.mark.xfail(reason="never executed on a GPU yet (written after the round-1 GPU budget was spent)", strict=False)
 from tests.test_docs_oracle import _write_reference_pickles, load_docs_golden
 from tests.test_gpu_models import ListReader, build
 
 
-@unverified
 @pytest.mark.gpu
 def test_load_data_from_reference_pickles(tmp_path):
     """readers.load_data == data.load_data over device-resident reviews: the train reader yields the golden
@@ -34,7 +28,6 @@ def test_load_data_from_reference_pickles(tmp_path):
     assert n_eval == len(z["eval_y"])
 
 
-@unverified
 @pytest.mark.gpu
 def test_train_complete_keeps_the_best_validation_checkpoint(tmp_path):
     """main.train_complete's contract (main.py:73-136): epochs of train -> validate, best-on-validation state_dict
@@ -61,7 +54,6 @@ def test_train_complete_keeps_the_best_validation_checkpoint(tmp_path):
     assert abs(m["MSE"] - min(logged)) < 1e-4
 
 
-@unverified
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["GMF", "MLP", "NeuMF"])
 def test_neumf_family_vs_reference(name):
@@ -90,7 +82,6 @@ def test_neumf_family_vs_reference(name):
         assert_close(sd[k], v, rtol=1e-4, atol=4e-6, msg="%s final.%s" % (name, k))
 
 
-@unverified
 @pytest.mark.gpu
 def test_neumf_init_fuses_the_pretrained_models():
     import reviews4rec_b200 as R
@@ -108,7 +99,6 @@ def test_neumf_init_fuses_the_pretrained_models():
             assert torch.equal(sd[k].cpu(), want[k]), k
 
 
-@unverified
 @pytest.mark.gpu
 @pytest.mark.parametrize("mt", ["deepconn", "NARRE"])
 def test_device_ranking_candidates_reproduce_reference_iter_negs(mt):
