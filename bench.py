@@ -1,23 +1,30 @@
 #!/usr/bin/env python
-"""bench.py -- train ratings/sec of the DeepCoNN rating-prediction hot path on B200.
+"""bench.py -- train ratings/sec of the rating-prediction hot path on B200.
 
-    python bench.py --gpus N --steps K --warmup W            (this repo's sm_100a path)
-    python bench.py --impl reference --gpus N --steps K --warmup W   (reference algorithm, host cores)
+    python bench.py [--model M] --gpus N --steps K --warmup W            (this repo's sm_100a path)
+    python bench.py [--model M] --impl reference --gpus N --steps K --warmup W   (reference algorithm, host cores)
 
-Workload = BASELINE.json configs[1]: DeepCoNN (`deepconn`, FM head), word_emb E=300, 100 conv
-filters, doc_len T=1000, latent 10, V=50,001 words, 1M users / 100k items, synthetic Amazon-shaped
-batches (reviews4rec_b200/synthetic.py).  A step = one training batch through main.train()'s body:
+Default workload = BASELINE.json configs[1]: DeepCoNN (`deepconn`, FM head), word_emb E=300, 100 conv filters,
+doc_len T=1000, latent 10, V=50,001 words, 1M users / 100k items, synthetic Amazon-shaped batches
+(reviews4rec_b200/synthetic.py).  --model NARRE = configs[3] (R=10 reviews x W=200 words, 500k users / 50k items),
+--model transnet++ = configs[4] (three towers, bf16 conv operands, restated three-loss step), --model deepconn++
+(MLP head + user / item bias tables under the dense Adam).  A step = one training batch through main.train()'s body:
 forward, per-sample squared error, backward, Adam (lr 0.002, weight_decay 1e-6, dropout 0.6).
 
 One JSON line on stdout (rank 0):
-  value     ratings/s with the batches already resident in HBM (a pool larger than L2, cycled)
-  e2e       ratings/s through the public API from pinned HOST batches: H2D of the batch and D2H of
-            the batch's squared-error sum are inside the timed region, every step
-  roofline  the dominant kernel (fused gather+conv+pool): algorithmic bytes per launch / its
-            CUDA-event duration inside the timed region, against MEASURED_PEAKS.json
-  cpu_baseline  the oracle's CPU restatement of the same step on a bounded sample (N=1 only)
+  value        ratings/s with the batches already resident in HBM (a pool larger than L2, cycled), CUDA-graph step
+  e2e          ratings/s through the public API from pinned HOST batches: H2D of the batch and D2H of the batch's
+               squared-error sum are inside the timed region, every step
+  eager        the drop-in path a maintainer of the reference would run: train.train(model, MSELoss, Adam, reader, hp)
+               (main.train's signature, Python-driven launches, no CUDA graph)
+  value_fp32   the same step with the fp32 CUDA-core conv (`exact` mode: reference precision), a few steps
+  precision    largest relative rating error of each conv mode against the fp32 oracle on a 64-rating sample
+  roofline     the dominant kernel (fused gather+conv+pool): executed FLOPs per launch / its CUDA-event duration
+               inside the timed region, against MEASURED_PEAKS.json; traffic from the committed ncu capture
+  cpu_baseline the oracle's CPU restatement of the same step on a bounded sample (N=1 only)
 """
 import argparse
+import importlib.util
 import json
 import os
 import pickle
@@ -32,35 +39,94 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 V_WORDS = 50001
-HP = {"model_type": "deepconn", "latent_size": 10, "word_embed_size": 300, "input_length": 1000, "dropout": 0.6,
-      "total_users": 1000000, "total_items": 100000, "lr": 0.002, "weight_decay": 1e-6, "batch_size": 4096,
-      "narre_num_reviews": 10, "narre_num_words": 200}
-METRIC = "train ratings/sec DeepCoNN synthetic Amazon-shape"
-# dram__bytes_read.sum + dram__bytes_write.sum of one conv_pool_tc launch at B=4096 (ncu --set full,
-# profiles/r1_v19_conv_ncu_raw.csv) and of one whole step (ncu launch list profiles/r1_v19_launches_bench.csv / 21 steps)
-NCU_CONV_DRAM_BYTES_PER_LAUNCH = 45.8e6
-NCU_STEP_DRAM_BYTES = 206.5e6
+BASE_HP = {"latent_size": 10, "word_embed_size": 300, "input_length": 1000, "dropout": 0.6, "lr": 0.002, "weight_decay": 1e-6,
+           "narre_num_reviews": 10, "narre_num_words": 200}
+# model -> (hyper_params overrides, ratings per GPU per step, default conv mode, workload text)
+MODELS = {
+    "deepconn": (dict(model_type="deepconn", total_users=1000000, total_items=100000), 4096, "f16",
+                 "DeepCoNN E=300 F=100 T=1000 L=10 V=50001 U=1M I=100k (BASELINE configs[1])"),
+    "deepconn++": (dict(model_type="deepconn++", total_users=1000000, total_items=100000), 4096, "f16",
+                   "DeepCoNN++ (MLP head + user/item bias tables) E=300 F=100 T=1000 L=10 V=50001 U=1M I=100k"),
+    "NARRE": (dict(model_type="NARRE", total_users=500000, total_items=50000, only_reviews=False), 2048, "f16",
+              "NARRE R=10 reviews x W=200 words, 10 neighbour ids, E=300 F=100 L=10 V=50001 U=500k I=50k (BASELINE configs[3])"),
+    "transnet++": (dict(model_type="transnet++", total_users=1000000, total_items=100000), 2048, "bf16",
+                   "TransNet++ three TextCNN towers, bf16 conv operands, E=300 F=100 T=1000 L=10 V=50001 U=1M I=100k (BASELINE configs[4])"),
+}
 REF_SAMPLE_B = 128            # ratings per reference-arm step (the reference's own default batch, hyper_params.py:60)
 
 
+def model_hp(name):
+    hp = dict(BASE_HP)
+    hp.update(MODELS[name][0])
+    return hp
+
+
+def metric_name(name):
+    return "train ratings/sec %s synthetic Amazon-shape" % {"deepconn": "DeepCoNN", "deepconn++": "DeepCoNN++", "NARRE": "NARRE",
+                                                             "transnet++": "TransNet++"}[name]
+
+
+def towers_of(hp):
+    """(documents per rating, rows per document) of the conv launches."""
+    mt = hp["model_type"]
+    if mt == "NARRE":
+        return 2 * hp["narre_num_reviews"], hp["narre_num_words"]
+    return (3 if mt.startswith("transnet") else 2), hp["input_length"]
+
+
 def algorithmic_bytes_per_rating(hp):
-    """bytes that must cross HBM once, as the reference stores them
-    (int64 token id + fp32 row per token, two docs; ids + rating + rating out)."""
-    T, E = hp["input_length"], hp["word_embed_size"]
-    return 2 * T * (8 + 4 * E) + 2 * 8 + 4 + 4
+    """bytes that must cross HBM once, as the reference stores them (int64 token id + fp32 row per
+    token; id rows; ids + rating + rating out)."""
+    mt, E, L = hp["model_type"], hp["word_embed_size"], hp["latent_size"]
+    docs, T = towers_of(hp)
+    words = docs * T * (8 + 4 * E)
+    if mt == "NARRE":
+        return words + 22 * (8 + 4 * L) + 22 * 2 * 4 * L + 24
+    if mt == "transnet++":
+        return words + 2 * (8 + 20) + 2 * 40 + 24
+    if mt == "deepconn++":
+        return words + 2 * (4 + 8) + 24
+    return words + 2 * 8 + 4 + 4
 
 
-def conv_flops_per_doc(hp):
-    return 2.0 * (hp["input_length"] + 2) * 100 * 3 * hp["word_embed_size"]
+def adam_stream_bytes_per_step(hp):
+    """SURVEY.md 8(d) per-step dense-Adam term: 7 streams x 4 B over every row of every id table the model trains."""
+    mt, L, U, I = hp["model_type"], hp["latent_size"], hp["total_users"] + 2, hp["total_items"] + 2
+    if mt == "deepconn++":
+        return (U + I) * 4 * 7
+    if mt == "NARRE":
+        return (U + I) * (L + 1) * 4 * 7
+    if mt == "transnet++":
+        return (U + I) * 5 * 4 * 7
+    return 0
 
 
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             m = json.load(f)
-        return float(m["hbm_gbs"]), float(m.get("bf16_tflops_sustained", m["bf16_tflops"])), "measured"
+        return float(m["hbm_gbs"]), float(m["bf16_tflops"]), float(m.get("bf16_tflops_sustained", m["bf16_tflops"])), "measured"
     except Exception:
-        return 6650.0, 1400.0, "fallback"
+        return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of ``kernel`` from the committed ncu capture
+    (profiles/ncu_traffic.json, written by scripts/ncu_summary.py from an `ncu --set full` run of this bench)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)["kernels"][kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+def load_synthetic():
+    """reviews4rec_b200/synthetic.py loaded BY PATH: the reference arm must not import the product package
+    (its __init__ maps libr4r_b200.so); the generator itself only needs numpy and torch."""
+    spec = importlib.util.spec_from_file_location("r4r_synthetic", os.path.join(ROOT, "reviews4rec_b200", "synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 class ClockSampler:
@@ -73,7 +139,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -87,14 +153,14 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
                 if len(f) < 9:
                     continue
                 try:
-                    sm.append(float(f[1])); mx.append(float(f[2]))
+                    sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
                 except ValueError:
                     continue
                 for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
@@ -104,31 +170,33 @@ class ClockSampler:
         except Exception:
             pass
         if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), power_w_max=max(pw), reasons=sorted(reasons), samples=len(sm))
         return out
 
 
 # ------------------------------------------------------------------------------------------ reference arm
-def oracle_params_from(model_state):
-    return {k: v.detach().to("cpu").clone() for k, v in model_state.items()}
-
-
 def cpu_train_rate(P, hp, n_steps, warmup, seed, budget_s=None):
-    """Times the oracle's restatement of main.train()'s batch body (oracle/r4r_oracle.py::train_batches,
-    same ATen CPU kernels the reference dispatches) on REF_SAMPLE_B-rating batches.  Returns (ratings/s, ms/step, steps)."""
-    import torch
+    """Times the oracle's restatement of main.train()'s batch body (oracle/r4r_oracle.py, the same ATen CPU kernels
+    the reference dispatches) on REF_SAMPLE_B-rating batches.  Returns (ratings/s, ms/step, steps)."""
     from oracle import r4r_oracle as O          # reference arm / cpu_baseline: the one place bench.py runs the oracle
-    from reviews4rec_b200.synthetic import SyntheticReader
+    S = load_synthetic()
     hp = dict(hp)
-    reader = SyntheticReader(hp, REF_SAMPLE_B, max(1, min(4, n_steps)), V_WORDS, seed=seed)
-    batches = reader.batches
-    opt = None
+    batches = S.SyntheticReader(hp, REF_SAMPLE_B, max(1, min(4, n_steps)), V_WORDS, seed=seed).batches
+    is_tn = hp["model_type"].startswith("transnet")
+    state = {"opt": None}
+
+    def one(b):
+        if is_tn:
+            state["opt"] = O.transnet_train(P, [b], hp, opts=state["opt"])[3]
+        else:
+            state["opt"] = O.train_batches(P, [b], hp, opt=state["opt"])[3]
+
     for i in range(warmup):
-        _, _, _, opt = O.train_batches(P, [batches[i % len(batches)]], hp, opt=opt)
+        one(batches[i % len(batches)])
     t0 = time.perf_counter()
     done = 0
     for i in range(n_steps):
-        _, _, _, opt = O.train_batches(P, [batches[i % len(batches)]], hp, opt=opt)
+        one(batches[i % len(batches)])
         done += 1
         if budget_s is not None and done >= 3 and time.perf_counter() - t0 > budget_s:
             break
@@ -144,15 +212,16 @@ def run_reference(args):
     from oracle import r4r_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    hp = dict(HP)
+    hp = model_hp(args.model)
     P = O.init_params(hp, V_WORDS, seed=1)
-    rate, ms, steps = cpu_train_rate(P, hp, args.steps, args.warmup, seed=1234)
+    rate, ms, steps = cpu_train_rate(P, hp, args.steps, args.warmup, seed=1234, budget_s=150.0)
     sample = "%d-rating batches (reference default batch_size) of the same synthetic workload, %d timed steps" % (REF_SAMPLE_B, steps)
-    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "ratings/s", "n_gpus": args.gpus, "steps": steps,
+    line = {"impl": "reference", "metric": metric_name(args.model), "value": rate, "unit": "ratings/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "DeepCoNN E=300 F=100 T=1000 L=10 V=50001 U=1M I=100k (BASELINE configs[1])",
-                       "batch": REF_SAMPLE_B, "threads": cores},
+            "config": {"workload": MODELS[args.model][3], "batch": REF_SAMPLE_B, "threads": cores,
+                       "implementation": "oracle/r4r_oracle.py (functional restatement of the reference's nn.Modules + main.train, pinned to "
+                                         "golden vectors of the unmodified reference; /root/reference cannot travel to the GPU box)"},
             "cpu_baseline": {"value": rate, "unit": "ratings/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "ratings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -170,18 +239,30 @@ def build_model(hp, device, seed):
         pickle.dump(np.zeros((V_WORDS, hp["word_embed_size"]), dtype=np.float32), f, 4)
     hp["data_dir"] = tmp
     torch.manual_seed(seed)
-    model = R.DeepCoNN(hp)
+    mt = hp["model_type"]
+    cls = R.NARRE if mt == "NARRE" else R.TransNet if mt.startswith("transnet") else R.DeepCoNN
+    model = cls(hp)
     xavier_init(model)                                                  # main.py:377
     return model.to(device)
 
 
+def make_optimizer(model, hp, capturable):
+    from reviews4rec_b200.optim import FusedAdam
+    from reviews4rec_b200.utils import init_transnet_optim
+    if hp["model_type"].startswith("transnet"):
+        cls = (lambda params, **kw: FusedAdam(params, capturable=capturable, **kw))
+        return init_transnet_optim(hp, model, cls)
+    return FusedAdam(model.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"], capturable=capturable)
+
+
 def run_b200(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
-    from reviews4rec_b200 import MSELoss, _lib, ops
-    from reviews4rec_b200.optim import FusedAdam
+    from reviews4rec_b200 import MSELoss, ops
+    from reviews4rec_b200.readers import RaggedReader
     from reviews4rec_b200.synthetic import SyntheticReader
-    from reviews4rec_b200.train import CapturedStep
+    from reviews4rec_b200.train import CapturedStep, train
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -198,13 +279,17 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
 
-    hp = dict(HP)
-    hp["batch_size"] = args.batch
-    B, K, W = args.batch, args.steps, max(args.warmup, 3)
-    ops.set_conv_mode(args.conv_mode)
+    hp = model_hp(args.model)
+    mt = hp["model_type"]
+    is_tn = mt.startswith("transnet")
+    B = args.batch or MODELS[args.model][1]
+    conv_mode = args.conv_mode or MODELS[args.model][2]
+    hp["batch_size"] = B
+    K, W = args.steps, max(args.warmup, 3)
+    ops.set_conv_mode(conv_mode)
     model = build_model(hp, dev, seed=1)                   # same seed on every rank: replicas start identical
     parallelism = "single GPU"
-    if world > 1 or args.force_shard:
+    if (world > 1 or args.force_shard) and not is_tn:
         # north_star: word + id tables row-sharded (row r on rank r % P), all-to-all index lookups;
         # ratings split across ranks (weak scaling), dense-gradient all-reduce inside the captured step
         from reviews4rec_b200 import sharded
@@ -217,57 +302,63 @@ def run_b200(args):
             world, ("word table row-sharded r%%P, per-step de-duplicated lookup over %s" % (
                 "NVLink peer stores (fused gather + all-to-all kernel)" if wtr else "NCCL all-to-all")) if args.table == "sharded"
             else "frozen word table replicated")
+    elif world > 1:
+        # TransNet's three optimizers step three disjoint parameter groups from one forward graph (main.py:35-53 restated);
+        # that schedule has no cross-rank exchange in it, so N GPUs run N independent replicas
+        group = None
+        parallelism = "replicas only: %d independent single-GPU training runs (no data-path collective)" % world
     model.train()
     criterion = MSELoss(hp)
-    opt = FusedAdam(model.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"], capturable=True)
+    opt = make_optimizer(model, hp, capturable=True)
 
     # ---- synthetic split, generated once on the host (numpy, seeded), as the eight arrays a..h of the reference's
     # quick-data format (make_quick_data.py:21-44); RaggedReader keeps it in pinned host memory
-    import numpy as np
-    from reviews4rec_b200.readers import RaggedReader
-    T = hp["input_length"]
+    docs_per_rating, T = towers_of(hp)
     ragged = args.docs == "ragged"
-    # resident pool larger than L2 (126 MB): padded int64 batches are 2*B*T*8 B; ragged ones ~0.2x that
-    per_batch = 2 * B * T * 8 * (0.21 if ragged else 1.0)
-    pool_n = max(2, min(12, -(-160 * 2 ** 20 // int(per_batch))))
+    per_batch = docs_per_rating * B * T * 8 * (0.21 if ragged else 1.0)
+    pool_n = max(2, min(12, -(-160 * 2 ** 20 // int(per_batch))))      # resident pool larger than L2 (126 MB)
     host = SyntheticReader(hp, B, pool_n, V_WORDS, seed=1234, device=None, pin=False, rank=rank)
-    cat = lambda j: np.concatenate([b_[0][j].numpy() for b_ in host.batches])
-    arrays = {k: None for k in "abcdefgh"}
-    arrays.update(d=cat(3), e=cat(4), f=cat(5), g=cat(6), h=np.concatenate([b_[1].numpy() for b_ in host.batches]))
+    cat = lambda j: None if host.batches[0][0][j] is None else np.concatenate([b_[0][j].numpy() for b_ in host.batches])
+    arrays = dict(zip("abcdefg", [cat(j) for j in range(7)]))
+    arrays["h"] = np.concatenate([b_[1].numpy() for b_ in host.batches])
     # the reader always hands ops.RaggedIdx documents over; --docs decides whether the kernels read them directly
     # ("ragged") or rebuild the padded int64 ids inside the captured step first ("padded", r4r_docs_expand)
     ops.set_ragged_native(ragged)
     rr = RaggedReader(hp, arrays, dev, native=True)
+    doc_slots = [j for j in (0, 3, 4) if host.batches[0][0][j] is not None]
 
     # ---- device-resident copies of every batch (the `value` measurement reads these)
-    class _Res:
-        batches = []
-    res = _Res()
-    resident_bytes = 0
+    res_batches, resident_bytes = [], 0
     for bi in range(pool_n):
         hd, hy = host.batches[bi]
+        data = [None if x is None else x.to(dev) for x in hd]
         if ragged:
-            docs = []
-            for k in ("d", "e"):
-                tok, off = rr.docs[k].batch_host(bi * B, (bi + 1) * B)
-                docs.append(ops.RaggedIdx(tok.to(dev), off.to(dev), (B, T), rr.docs[k].pad_id))
-                resident_bytes += tok.numel() * 4 + off.numel() * 8
+            for j, k in ((0, "a"), (3, "d"), (4, "e")):
+                if hd[j] is not None:
+                    tok, off = rr.docs[k].batch_host(bi * B, (bi + 1) * B)
+                    data[j] = ops.RaggedIdx(tok.to(dev), off.to(dev), tuple(hd[j].shape), rr.docs[k].pad_id)
+                    resident_bytes += tok.numel() * 4 + off.numel() * 8
         else:
-            docs = [hd[3].to(dev), hd[4].to(dev)]
-            resident_bytes += 2 * B * T * 8
-        res.batches.append(([None, None, None, docs[0], docs[1], hd[5].to(dev), hd[6].to(dev)], hy.to(dev)))
+            resident_bytes += sum(hd[j].numel() * 8 for j in doc_slots)
+        res_batches.append((data, hy.to(dev)))
 
     # conv positions the launches actually process (documents cut to their informative prefix, exact)
-    pos_sum = 0
-    for d, _ in res.batches:
-        for idx in (d[3], d[4]):
-            pos_sum += int(ops.doc_lengths(idx).sum().item()) + 2 * idx.shape[0]
-    positions_per_launch = pos_sum / (2.0 * len(res.batches)) if ops.get_doc_plan() else float(B * (T + 2))
+    pos_sum, n_docs = 0, 0
+    plan_on = ops.get_doc_plan() and T + 2 > 256
+    for d, _ in res_batches:
+        for j in doc_slots:
+            idx = d[j] if isinstance(d[j], ops.RaggedIdx) else d[j].reshape(-1, T)
+            rows = int(idx.shape[0]) if not isinstance(idx, ops.RaggedIdx) else int(np.prod(idx.shape[:-1]))
+            pos_sum += (int(ops.doc_lengths(idx).sum().item()) if plan_on else rows * T) + 2 * rows
+            n_docs += rows
+    n_towers = len(doc_slots)
+    positions_per_launch = pos_sum / float(n_towers * len(res_batches))
+    docs_per_launch = n_docs / float(n_towers * len(res_batches))
 
     se_sum = torch.zeros(1, device=dev, dtype=torch.float32)
     conv_events = []
     ops.set_conv_event_sink(conv_events)
-    steps_res = [CapturedStep(model, criterion, opt, d, y, se_sum, group, float(world)) for d, y in res.batches]
+    steps_res = [CapturedStep(model, criterion, opt, d, y, se_sum, group, float(world)) for d, y in res_batches]
     launches_per_step = steps_res[0].launches              # this library's kernels inside one captured step
     res_events = list(conv_events)
     ops.set_conv_event_sink(None)
@@ -276,6 +367,12 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def reduce_max(*vals):
+        t = torch.tensor(list(vals), device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
 
     # ---- value: device-resident inputs
     for i in range(W):
@@ -290,31 +387,25 @@ def run_b200(args):
         steps_res[i % pool_n].replay()
     e1.record()
     barrier()
-    ms_total = e0.elapsed_time(e1)
+    (ms_total,) = reduce_max(e0.elapsed_time(e1))
     train_mse = float(se_sum.item()) / (K * B)
+    value = world * B * K / (ms_total * 1e-3)
     # dominant kernel: duration of its launches in the last min(K, pool) steps of the timed region
     used = min(K, pool_n)
     conv_ms = []
     try:
+        per = len(res_events) // pool_n                         # eager warm pass + captured pass per slot; the captured launches are last
         for j in range(used):
             slot = (K - 1 - j) % pool_n
-            per = len(res_events) // pool_n                     # eager warm pass + captured pass per slot; the captured pair is last
-            for a, b in res_events[per * slot + per - 2: per * slot + per]:
+            for a, b in res_events[per * slot + per - n_towers: per * slot + per]:
                 conv_ms.append(a.elapsed_time(b))
-    except Exception as exc:                                       # external event nodes unsupported -> measured below
+    except Exception:                                             # external event nodes unsupported -> measured below
         conv_ms = []
-        conv_err = repr(exc)
-    clocks = sampler.stop() if sampler else None
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    value = world * B * K / (ms_total * 1e-3)
 
     # ---- e2e through the public API: RaggedReader (this repo's counterpart of data_fast.DataLoader) holds the
     # split in pinned HOST memory -- int32 tokens up to each document's trailing padding run -- and per step copies
-    # a batch H2D (copy stream, double-buffered) into the buffers the captured step reads (as ops.RaggedIdx
-    # documents, or expanded to padded int64 with --docs padded); the running SE sum is read back D2H every step.
+    # a batch H2D (copy stream, double-buffered) into the buffers the captured step reads; the running SE sum is
+    # read back D2H every step.
     main = torch.cuda.current_stream()
     se_e2e = torch.zeros(1, device=dev, dtype=torch.float32)
     steps_e2e = []
@@ -330,144 +421,166 @@ def run_b200(args):
     def e2e_loop(n):
         for i in range(n):
             s_ = i & 1
-            rr.stage(i % pool_n, s_)                              # H2D of the ragged batch + expansion, on the copy stream
+            rr.stage(i % pool_n, s_)                              # H2D of the ragged batch, on the copy stream
             h2d_log.append(rr.h2d_bytes_last)
             rr.wait_ready(s_, main)
             steps_e2e[s_].replay()
             rr.release(s_, main)
             se_host[i:i + 1].copy_(se_e2e, non_blocking=True)     # running SE sum, read back every step (main.py:57)
 
-    def timed(loop):
-        loop(W)
+    def timed(loop, n):
+        loop(min(W, n))
         barrier()
         se_e2e.zero_()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         e0.record()
-        loop(K)
+        loop(n)
         e1.record()
         barrier()
         wall = (time.perf_counter() - t0) * 1e3
-        tt = torch.tensor([max(e0.elapsed_time(e1), 0.0), wall], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt[0].item()), float(tt[1].item())
+        return reduce_max(max(e0.elapsed_time(e1), 0.0), wall)
 
-    e2e_ms, e2e_wall = timed(e2e_loop)
+    e2e_ms, e2e_wall = timed(e2e_loop, K)
     h2d = int(sum(h2d_log[-K:]) / K)
     e2e_value = world * B * K / (e2e_ms * 1e-3)
 
-    # ---- the same with the batches shipped as the reference's reader does: padded int64 [B,T] from pinned host memory
-    if True:
-        pstatic = [([None, None, None] + [torch.empty(B, T, device=dev, dtype=torch.int64) for _ in range(2)]
-                    + [torch.empty(B, device=dev, dtype=torch.int64) for _ in range(2)],
-                    torch.empty(B, device=dev, dtype=torch.float32)) for _ in range(2)]
-        for (pd, py), (hd, hy) in zip(pstatic, host.batches):
-            for dst, src in zip(pd, hd):
-                if dst is not None:
-                    dst.copy_(src)
-            py.copy_(hy)
-        steps_pad = [CapturedStep(model, criterion, opt, pd, py, se_e2e, group, float(world)) for pd, py in pstatic]
-        hpin = [([None if x is None else x.pin_memory() for x in hd], hy.pin_memory()) for hd, hy in host.batches[:3]]
-    copy_stream = torch.cuda.Stream()
-    ready = [torch.cuda.Event() for _ in range(2)]
-    done = [torch.cuda.Event() for _ in range(2)]
+    # ---- the drop-in path: the eager loop with main.train's signature over device-resident batches (what a
+    # maintainer gets from the import swap of INTEGRATION.md alone: Python-driven launches, no CUDA graph)
+    class _Pool:
+        def __init__(self, n):
+            self.n = n
 
-    def padded_loop(n):
-        for i in range(n):
-            s_ = i & 1
-            hd, hy = hpin[i % len(hpin)]
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(done[s_])
-                for dst, src in zip(pstatic[s_][0], hd):
-                    if dst is not None:
-                        dst.copy_(src, non_blocking=True)
-                pstatic[s_][1].copy_(hy, non_blocking=True)
-                ready[s_].record(copy_stream)
-            main.wait_event(ready[s_])
-            steps_pad[s_].replay()
-            done[s_].record(main)
-            se_host[i:i + 1].copy_(se_e2e, non_blocking=True)
+        def __len__(self):
+            return self.n
 
-    pad_ms, _ = timed(padded_loop)
-    pad_value = world * B * K / (pad_ms * 1e-3)
-    t = torch.tensor([e2e_ms, e2e_wall], dtype=torch.float64)
+        def iter(self, eval=False):
+            for i in range(self.n):
+                yield res_batches[i % pool_n]
+
+    eager = None
+    if not args.no_eager:
+        Ke = max(3, min(K, 60))
+        opt_e = make_optimizer(model, hp, capturable=False)
+        train(model, criterion, opt_e, _Pool(3), hp)
+        barrier()
+        e0.record()
+        m_e = train(model, criterion, opt_e, _Pool(Ke), hp)
+        e1.record()
+        barrier()
+        (eager_ms,) = reduce_max(e0.elapsed_time(e1))
+        eager = {"value": world * B * Ke / (eager_ms * 1e-3), "unit": "ratings/s", "ms_per_step": eager_ms / Ke, "steps": Ke,
+                 "api": "reviews4rec_b200.train.train(model, MSELoss, FusedAdam, reader, hyper_params) -- main.train's signature (main.py:8-71), "
+                        "eager Python loop, device-resident batches", "train_mse": m_e["MSE"]}
+    clocks = sampler.stop() if sampler else None
+
+    # ---- reference precision: the same captured step with the fp32 CUDA-core conv (`exact` mode), a few steps;
+    # and the largest relative rating error of each conv mode against the fp32 oracle on a 64-rating sample
+    value_fp32, precision = None, None
+    if world == 1 and not args.no_fp32 and conv_mode != "exact":
+        ops.set_conv_mode("exact")
+        opt32 = make_optimizer(model, hp, capturable=True)
+        se32 = torch.zeros(1, device=dev, dtype=torch.float32)
+        steps32 = [CapturedStep(model, criterion, opt32, d, y, se32, None, 1.0) for d, y in res_batches[:2]]
+        K32 = 4
+        steps32[0].replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(K32):
+            steps32[i % 2].replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms32 = e0.elapsed_time(e1) / K32
+        value_fp32 = {"value": B / (ms32 * 1e-3), "unit": "ratings/s", "ms_per_step": ms32, "steps": K32, "dtype": "f32",
+                      "note": "conv on CUDA cores in fp32 (r4r_conv_pool_simt), everything else identical; device-resident inputs"}
+        del steps32
+        ops.set_conv_mode(conv_mode)
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import r4r_oracle as O          # checker leg (precision + cpu_baseline), never the product path
+        P = {k: v.detach().to("cpu").clone() for k, v in model.state_dict().items()}
+        hd, hy = host.batches[0]
+        sample = [None if x is None else x[:64] for x in hd]
+        with torch.no_grad():
+            ref = O.forward(P, sample, hp, train=False)
+            ref = ref[0] if isinstance(ref, list) else ref
+            precision = {}
+            model.eval()
+            for m in ("exact", "f16", "bf16"):
+                ops.set_conv_mode(m)
+                out = model([None if x is None else x.to(dev) for x in sample])
+                out = (out[0] if isinstance(out, list) else out).cpu()
+                precision[m] = float(((out - ref).abs() / ref.abs()).max())
+            model.train()
+            ops.set_conv_mode(conv_mode)
+        precision["sample"] = "64 ratings of the bench workload, eval forward, trained parameters of this run, vs oracle fp32 on the host"
 
     # ---- dominant kernel timed stand-alone if the in-graph events were unavailable
     timing = "cuda events bracketing the kernel inside the captured step, last %d steps of the timed region" % used
-    if not conv_ms and world > 1:
-        conv_ms = [float("nan")]
     if not conv_ms:
-        d, y = res.batches[0]
-        conv = model.user_conv.convs[0]
-        with torch.no_grad():
-            for i in range(3):
-                ops.conv_pool_forward(d[3], model.word2vec.weight, conv.weight, conv.bias, args.conv_mode, model.word2vec._shadow)
-            for i in range(min(K, pool_n)):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                sink = []
-                ops.set_conv_event_sink(sink)
-                ops.conv_pool_forward(res.batches[i][0][3], model.word2vec.weight, conv.weight, conv.bias, args.conv_mode, model.word2vec._shadow)
-                ops.set_conv_event_sink(None)
-                torch.cuda.synchronize()
-                conv_ms.append(sink[0][0].elapsed_time(sink[0][1]))
-        timing = "cuda events around stand-alone launches on the bench batches (in-graph events unavailable)"
+        conv_ms = [float("nan")]
+        timing = "unavailable (in-graph event nodes not supported here)"
 
     if rank != 0:
         _finish(world)
         return
 
-    hbm_peak, tf_peak, peak_kind = measured_peaks()
+    hbm_peak, tf_burst, tf_sustained, peak_kind = measured_peaks()
     conv_avg_ms = sum(conv_ms) / len(conv_ms)
     step_ms = ms_total / K
-    E, T = hp["word_embed_size"], hp["input_length"]
+    E = hp["word_embed_size"]
     # FLOPs one launch executes: sum over its documents of (informative rows + 2 conv positions) x F x 3E x 2
     # (the padding-run shortcut is exact); algorithmic = the reference's dense conv over all T+2 positions
     exec_flops = positions_per_launch * 100 * 3 * E * 2.0
-    alg_flops = B * conv_flops_per_doc(hp)
+    alg_flops = docs_per_launch * 2.0 * (T + 2) * 100 * 3 * E
     tflops = exec_flops / (conv_avg_ms * 1e-3) / 1e12
-    alg_bytes_launch = B * T * (8 + 4 * E)                           # one tower = one doc per rating, reference storage
+    alg_bytes_launch = docs_per_launch * T * (8 + 4 * E)             # one launch = one tower, reference storage
+    conv_kernel = "conv_pool_simt_kernel" if conv_mode == "exact" else "conv_pool_tc_kernel"
+    bpr, adam_b = algorithmic_bytes_per_rating(hp), adam_stream_bytes_per_step(hp)
+    step_gbs = (bpr * value / world + adam_b * (value / world / B)) / 1e9
     line = {
-        "metric": METRIC, "value": value, "unit": "ratings/s", "n_gpus": world, "steps": K, "warmup": W,
+        "metric": metric_name(args.model), "value": value, "unit": "ratings/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"f16": "f16", "bf16": "bf16", "exact": "f32"}[args.conv_mode],
+        "dtype": {"f16": "f16", "bf16": "bf16", "exact": "f32"}[conv_mode],
         "data": "synthetic",
-        "config": {"workload": "DeepCoNN E=300 F=100 T=1000 L=10 V=50001 U=1M I=100k (BASELINE configs[1])",
-                   "batch_per_gpu": B, "global_batch": B * world, "conv_mode": args.conv_mode, "dropout": hp["dropout"],
+        "config": {"workload": MODELS[args.model][3],
+                   "batch_per_gpu": B, "global_batch": B * world, "conv_mode": conv_mode, "dropout": hp["dropout"],
                    "arithmetic": {"f16": "conv operands f16 (private shadow of the frozen word table + packed filters), fp32 accumulation in TMEM; everything else fp32",
                                   "bf16": "conv operands bf16, fp32 accumulation in TMEM; everything else fp32",
-                                  "exact": "fp32 everywhere (CUDA-core conv)"}[args.conv_mode],
+                                  "exact": "fp32 everywhere (CUDA-core conv)"}[conv_mode],
                    "parallelism": parallelism,
                    "documents": ("ragged on the device (ops.RaggedIdx: int32 tokens before each trailing padding run + offsets); "
                                  "same padded documents as the reference's reader, never materialised") if ragged
-                                else "padded int64 [B,T] as the reference's reader yields them",
+                                else "padded int64 as the reference's reader yields them",
                    "l2_policy": "inputs larger than L2: %d resident batches, %.0f MB in total, cycled" % (pool_n, resident_bytes / 2 ** 20),
-                   "step": "CUDA graph of zero_grad+forward+MSE+backward+Adam"},
+                   "step": "CUDA graph of zero_grad+forward+MSE+backward+Adam" + (" (restated three-loss TransNet step, three optimizers)" if is_tn else "")},
         "e2e": {"value": e2e_value, "unit": "ratings/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "ms_per_step": e2e_ms / K, "wall_ms_per_step": float(t[1].item()) / K,
+                "ms_per_step": e2e_ms / K, "wall_ms_per_step": e2e_wall / K,
                 "api": "readers.RaggedReader (pinned host split: int32 tokens before each document's trailing padding run) "
                        "-> H2D -> ops.RaggedIdx -> train.CapturedStep (%s)" % (
-                           "kernels read the ragged tokens" if ragged else "r4r_docs_expand rebuilds the padded int64 ids inside the captured step"),
-                "padded_int64_reader": {"value": pad_value, "ms_per_step": pad_ms / K, "h2d_bytes_per_step": 2 * B * T * 8 + 2 * B * 8 + B * 4,
-                                        "note": "batches shipped as data_fast.py does: padded int64 [B,T] per document, PCIe-bound"}},
+                           "kernels read the ragged tokens" if ragged else "r4r_docs_expand rebuilds the padded int64 ids inside the captured step")},
+        "eager": eager,
+        "value_fp32": value_fp32,
+        "precision": precision,
         "gpu_launches": launches_per_step * K,
-        "roofline": {"kernel": "conv_pool_tc_kernel (fused word gather + TextCNN conv + ReLU + max-pool), tcgen05 cta_group::2",
-                     "bound": "tensor", "achieved": tflops, "peak": tf_peak, "unit": "TFLOP/s", "frac": tflops / tf_peak,
-                     "traffic": NCU_CONV_DRAM_BYTES_PER_LAUNCH if (B == 4096 and world == 1) else None,
-                     "peak_kind": peak_kind + " (cuBLAS bf16, sustained)", "ms_per_launch": conv_avg_ms, "launches_per_step": 2,
-                     "share_of_step": 2 * conv_avg_ms / step_ms, "timing": timing,
-                     "executed_flops_per_launch": exec_flops, "mean_informative_rows_per_doc": positions_per_launch / B - 2,
+        "roofline": {"kernel": "%s (fused word gather + TextCNN conv + ReLU + max-pool)%s" % (
+                         conv_kernel, "" if conv_mode == "exact" else ", tcgen05 cta_group::2"),
+                     "bound": "tensor", "achieved": tflops, "peak": tf_burst, "unit": "TFLOP/s", "frac": tflops / tf_burst,
+                     "traffic": ncu_traffic(conv_kernel) if (args.model == "deepconn" and B == 4096 and world == 1) else None,
+                     "peak_kind": peak_kind + " (cuBLAS bf16 burst: the timed region is far shorter than the power-capped sustained regime)",
+                     "frac_of_sustained_peak": tflops / tf_sustained,
+                     "ms_per_launch": conv_avg_ms, "launches_per_step": n_towers,
+                     "share_of_step": n_towers * conv_avg_ms / step_ms, "timing": timing,
+                     "executed_flops_per_launch": exec_flops, "mean_informative_rows_per_doc": positions_per_launch / docs_per_launch - 2,
                      "algorithmic_flops_per_launch": alg_flops, "algorithmic_tflops": alg_flops / (conv_avg_ms * 1e-3) / 1e12,
                      "algorithmic_bytes_per_launch": alg_bytes_launch,
                      "algorithmic_gbs": alg_bytes_launch / (conv_avg_ms * 1e-3) / 1e9,
                      "note": "achieved = executed FLOPs (exact padding-run shortcut applied) / event time; "
                              "algorithmic_* = the reference's dense work (all T+2 positions, fp32 rows + int64 ids) / the same time"},
-        "step_roofline": {"bytes_per_rating": algorithmic_bytes_per_rating(hp),
-                          "achieved_gbs": algorithmic_bytes_per_rating(hp) * value / world / 1e9,
-                          "frac_of_hbm_peak": algorithmic_bytes_per_rating(hp) * value / world / 1e9 / hbm_peak,
-                          "traffic_per_step": NCU_STEP_DRAM_BYTES if (B == 4096 and world == 1) else None,
-                          "note": "algorithmic bytes as the reference stores them (fp32 rows + int64 ids, SURVEY.md 8d); the step "
-                                  "actually moves traffic_per_step bytes of DRAM (frozen table in half precision, L2-resident), "
+        "step_roofline": {"bytes_per_rating": bpr, "adam_stream_bytes_per_step": adam_b,
+                          "achieved_gbs": step_gbs, "frac_of_hbm_peak": step_gbs / hbm_peak,
+                          "traffic_per_step": ncu_traffic("__step__") if (args.model == "deepconn" and B == 4096 and world == 1) else None,
+                          "note": "algorithmic bytes as the reference stores them (fp32 rows + int64 ids, SURVEY.md 8d) plus the dense-Adam stream; "
+                                  "the step actually moves traffic_per_step bytes of DRAM (frozen table in half precision, L2-resident), "
                                   "which is why the fraction can exceed 1"},
         "train_mse": train_mse,
         "clocks": clocks,
@@ -475,10 +588,10 @@ def run_b200(args):
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        P = oracle_params_from(model.state_dict())
+        P = {k: v.detach().to("cpu").clone() for k, v in model.state_dict().items()}
         rate, ms, steps = cpu_train_rate(P, hp, 40, 1, seed=1234, budget_s=15.0)
         line["cpu_baseline"] = {"value": rate, "unit": "ratings/s", "cores": cores, "kind": "port",
-                                "sample": "%d timed steps of %d ratings (same synthetic workload), oracle/r4r_oracle.py::train_batches" % (steps, REF_SAMPLE_B)}
+                                "sample": "%d timed steps of %d ratings (same synthetic workload), oracle/r4r_oracle.py" % (steps, REF_SAMPLE_B)}
     print(json.dumps(line), flush=True)
     _finish(world)
 
@@ -500,9 +613,12 @@ def main():
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=HP["batch_size"], help="ratings per GPU per step")
-    ap.add_argument("--conv-mode", default="f16", choices=["f16", "bf16", "exact"])
+    ap.add_argument("--model", default="deepconn", choices=sorted(MODELS))
+    ap.add_argument("--batch", type=int, default=0, help="ratings per GPU per step (default: per model)")
+    ap.add_argument("--conv-mode", default=None, choices=["f16", "bf16", "exact"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager", action="store_true")
+    ap.add_argument("--no-fp32", action="store_true")
     ap.add_argument("--docs", default="padded", choices=["ragged", "padded"],
                     help="how the reader hands documents to the model: padded int64 tensors rebuilt on the device (default) or ops.RaggedIdx")
     ap.add_argument("--table", default="sharded", choices=["sharded", "replicated"], help="word table placement for --gpus > 1")

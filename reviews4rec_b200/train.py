@@ -128,8 +128,9 @@ def train_complete(hyper_params, Model, train_reader, val_reader, user_count, it
 
 
 class CapturedStep:
-    """One non-TransNet training batch of ``train()`` -- zero_grad, forward, per-sample SE, backward
-    of the mean, optional data-parallel gradient all-reduce, optimizer step (main.py:26-60) --
+    """One training batch of ``train()`` -- zero_grad, forward, per-sample SE, backward of the mean,
+    optional data-parallel gradient all-reduce, optimizer step (main.py:26-60; for TransNet the restated
+    three-loss step of ``transnet_step`` with the optimizer triple of ``utils.init_transnet_optim``) --
     recorded ONCE into a CUDA graph over static input buffers and replayed per batch, so a step
     costs one graph launch instead of ~40 Python-driven kernel launches.
 
@@ -143,8 +144,11 @@ class CapturedStep:
         self.model, self.data, self.y = model, data, y
         dev = y.device
         self.se_sum = se_sum if se_sum is not None else torch.zeros(1, device=dev, dtype=torch.float32)
-        if hasattr(optimizer, "prepare"):
-            optimizer.prepare()
+        hp = getattr(model, "hyper_params", {})
+        is_tn = hp.get("model_type") in TRANSNET
+        for o in (optimizer if isinstance(optimizer, (list, tuple)) else [optimizer]):
+            if hasattr(o, "prepare"):
+                o.prepare()
         with torch.no_grad():
             model(data)             # eager pass: builds the shadow word table and lazy kernel attributes outside the graph
         model.zero_grad(set_to_none=True)
@@ -154,16 +158,23 @@ class CapturedStep:
         launches0 = _lib.launch_count
         with torch.cuda.graph(self.graph):
             ops.arena_begin(dev)                    # one memset for all the zeroed gradient buffers of the step
-            out = model(data)
-            se = criterion(out, y, return_mean=False)
-            self.se_sum += se.detach().sum()
-            torch.mean(se).backward()
-            if group is not None:
-                # replicated parameters: mean over ranks; row-sharded tables already received their
-                # rows' gradients from every rank inside the backward (sharded.py)
-                from .sharded import allreduce_dense_grads
-                allreduce_dense_grads(model, group, int(grad_div))
-            optimizer.step()
+            if is_tn:
+                if group is not None:
+                    raise RuntimeError("CapturedStep: the TransNet three-loss step is single-process (replicas only)")
+                se, _, _ = transnet_step(model, criterion, optimizer, data, y, hp)
+                self.se_sum += se.sum()
+                out = None
+            else:
+                out = model(data)
+                se = criterion(out, y, return_mean=False)
+                self.se_sum += se.detach().sum()
+                torch.mean(se).backward()
+                if group is not None:
+                    # replicated parameters: mean over ranks; row-sharded tables already received their
+                    # rows' gradients from every rank inside the backward (sharded.py)
+                    from .sharded import allreduce_dense_grads
+                    allreduce_dense_grads(model, group, int(grad_div))
+                optimizer.step()
             ops.arena_end()
         self.launches = _lib.launch_count - launches0       # kernels of this library one replay launches
         self.out = out

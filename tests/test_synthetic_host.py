@@ -29,8 +29,26 @@ def test_synthetic_batches_follow_the_survey_spec():
 
 def test_contract_figures():
     import bench
-    hp = dict(bench.HP)
-    assert bench.algorithmic_bytes_per_rating(hp) == 2416024              # SURVEY.md 8(d)
-    assert abs(bench.conv_flops_per_doc(hp) - 180.36e6) < 0.01e6          # 2 * 1002 * 100 * 900
+    hp = bench.model_hp("deepconn")
+    assert bench.algorithmic_bytes_per_rating(hp) == 2416024                              # SURVEY.md 8(d)
+    assert bench.algorithmic_bytes_per_rating(bench.model_hp("NARRE")) == 4834840
+    assert bench.algorithmic_bytes_per_rating(bench.model_hp("transnet++")) == 3624160
+    assert bench.adam_stream_bytes_per_step(bench.model_hp("deepconn++")) == (1000002 + 100002) * 4 * 7      # 30.8 MB
+    assert bench.adam_stream_bytes_per_step(bench.model_hp("NARRE")) == (500002 + 50002) * 11 * 4 * 7       # 169 MB
+    assert bench.towers_of(hp) == (2, 1000) and bench.towers_of(bench.model_hp("NARRE")) == (20, 200)
     assert bench.V_WORDS == 50001 and hp["total_users"] == 1000000 and hp["total_items"] == 100000
     assert hp["word_embed_size"] == 300 and hp["input_length"] == 1000 and hp["latent_size"] == 10
+
+
+def test_reference_arm_does_not_load_the_product():
+    """`bench.py --impl reference` must not import reviews4rec_b200 (whose __init__ maps libr4r_b200.so): it loads
+    the synthetic generator by path and runs only the oracle."""
+    import subprocess
+    import sys
+    code = ("import sys, bench; S = bench.load_synthetic(); import oracle.r4r_oracle; "
+            "bad = [m for m in sys.modules if m.startswith('reviews4rec_b200')]; "
+            "assert not bad, bad; assert hasattr(S, 'SyntheticReader'); print('clean')")
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True)
+    assert out.returncode == 0 and "clean" in out.stdout, out.stderr
