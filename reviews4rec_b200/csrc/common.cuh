@@ -58,6 +58,14 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// vector reductions into global memory (sm_90+): one L2 atomic transaction for 2 / 4 consecutive floats
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" :: "l"(p), "f"(a), "f"(b) : "memory");
+}
+
 // streaming 128-bit global accesses (Guideline 13: L1::no_allocate for data touched once)
 __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
   float4 r;

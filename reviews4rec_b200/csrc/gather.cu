@@ -76,18 +76,21 @@ extern "C" int r4r_shadow_build(const float* table, int64_t V, int E, void* shad
 }
 
 // ------------------------------------------------------------------------------------------
-// K5: L is small (1..64): one thread per (row, column) element, consecutive threads -> consecutive
-// columns of one gathered row.
+// K5: one thread per (row, 16-byte chunk) when rows are whole float4s, else per (row, column) element;
+// consecutive threads -> consecutive chunks of one gathered row.
+template <int W>
 __global__ void __launch_bounds__(256) rows_gather_kernel(const float* __restrict__ table, int64_t R, int L,
                                                           const int64_t* __restrict__ ids, int64_t n,
                                                           float* __restrict__ out) {
-  const int64_t total = n * (int64_t)L;
+  const int lw = L / W;
+  const int64_t total = n * (int64_t)lw;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = i / L;
-    int c = (int)(i - r * L);
+    int64_t r = i / lw;
+    int c = (int)(i - r * lw);
     int64_t id = __ldg(ids + r);
     if (id < 0 || id >= R) __trap();
-    out[i] = __ldg(table + id * (int64_t)L + c);
+    if constexpr (W == 4) reinterpret_cast<float4*>(out)[i] = __ldg(reinterpret_cast<const float4*>(table + id * (int64_t)L) + c);
+    else out[i] = __ldg(table + id * (int64_t)L + c);
   }
 }
 
@@ -95,17 +98,21 @@ extern "C" int r4r_rows_gather(const float* table, int64_t R, int L, const int64
   R4R_REQUIRE(table && ids && out, R4R_EINVAL, "rows_gather: null pointer");
   R4R_REQUIRE(R > 0 && L > 0 && n >= 0, R4R_EINVAL, "rows_gather: bad sizes");
   if (n == 0) return 0;
-  int64_t blocks = cdiv64(n * (int64_t)L, 256);
+  const bool v4 = L % 4 == 0 && ((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(out)) % 16 == 0);
+  int64_t blocks = cdiv64(n * (int64_t)(v4 ? L / 4 : L), 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  rows_gather_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(table, R, L, ids, n, out);
+  if (v4) rows_gather_kernel<4><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(table, R, L, ids, n, out);
+  else rows_gather_kernel<1><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(table, R, L, ids, n, out);
   R4R_CHECK_LAUNCH("rows_gather");
   return 0;
 }
 
 // K6: one lane per batch row.  Lanes of a warp that target the same table row are found with
-// match.any; the lowest such lane sums the group's rows column by column and issues ONE
-// atomicAdd per column, so a hot row (NARRE's pad id) costs one atomic per warp
-// instead of 32.
+// match.any; the lowest such lane sums the group's rows and issues ONE reduction per W consecutive
+// columns (W = 4 / 2 / 1: red.global.add.v4 / .v2 / scalar -- one L2 atomic transaction each), so a hot
+// row (NARRE's pad id) costs one atomic per warp instead of 32 and a 32-column row costs
+// 8 transactions instead of 32.
+template <int W>
 __global__ void __launch_bounds__(256) rows_scatter_add_kernel(const float* __restrict__ gout,
                                                                const int64_t* __restrict__ ids, int64_t n, int L,
                                                                float* __restrict__ gtable, int64_t R) {
@@ -118,17 +125,40 @@ __global__ void __launch_bounds__(256) rows_scatter_add_kernel(const float* __re
     if (valid && (id < 0 || id >= R)) __trap();
     unsigned grp = __match_any_sync(0xffffffffu, id);
     int leader = __ffs(grp) - 1;
-    for (int c = 0; c < L; ++c) {
-      float g = valid ? __ldg(gout + i * (int64_t)L + c) : 0.0f;
-      // segmented sum over the lanes in `grp`, accumulated at the leader
-      float s = 0.0f;
-      unsigned rem = grp;
-      while (rem) {                                      // uniform within the group
-        int src = __ffs(rem) - 1;
-        s += __shfl_sync(grp, g, src);
-        rem &= rem - 1;
+    const bool single = grp == (1u << lane);             // the common case: nobody else in the warp hits this row
+    for (int c = 0; c < L; c += W) {
+      float g[W];
+      if constexpr (W == 4) {
+        float4 t = valid ? __ldg(reinterpret_cast<const float4*>(gout + i * (int64_t)L + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
+      } else if constexpr (W == 2) {
+        float2 t = valid ? __ldg(reinterpret_cast<const float2*>(gout + i * (int64_t)L + c)) : make_float2(0.f, 0.f);
+        g[0] = t.x; g[1] = t.y;
+      } else {
+        g[0] = valid ? __ldg(gout + i * (int64_t)L + c) : 0.0f;
       }
-      if (valid && lane == leader) atomicAdd(gtable + id * (int64_t)L + c, s);
+      float s[W];
+      if (__all_sync(0xffffffffu, single)) {             // warp-uniform fast path: no duplicates in this warp
+#pragma unroll
+        for (int k = 0; k < W; ++k) s[k] = g[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < W; ++k) s[k] = 0.0f;
+        // segmented sum over the lanes in `grp`, accumulated at the leader
+        unsigned rem = grp;
+        while (rem) {                                      // uniform within the group
+          int src = __ffs(rem) - 1;
+#pragma unroll
+          for (int k = 0; k < W; ++k) s[k] += __shfl_sync(grp, g[k], src);
+          rem &= rem - 1;
+        }
+      }
+      if (valid && lane == leader) {
+        float* dst = gtable + id * (int64_t)L + c;
+        if constexpr (W == 4) red_add_v4(dst, s[0], s[1], s[2], s[3]);
+        else if constexpr (W == 2) red_add_v2(dst, s[0], s[1]);
+        else atomicAdd(dst, s[0]);
+      }
     }
   }
 }
@@ -139,7 +169,10 @@ extern "C" int r4r_rows_scatter_add(const float* gout, const int64_t* ids, int64
   if (n == 0) return 0;
   int64_t blocks = cdiv64(n, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  rows_scatter_add_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(gout, ids, n, L, gtable, R);
+  const uintptr_t al = reinterpret_cast<uintptr_t>(gout) | reinterpret_cast<uintptr_t>(gtable);
+  if (L % 4 == 0 && al % 16 == 0) rows_scatter_add_kernel<4><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(gout, ids, n, L, gtable, R);
+  else if (L % 2 == 0 && al % 8 == 0) rows_scatter_add_kernel<2><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(gout, ids, n, L, gtable, R);
+  else rows_scatter_add_kernel<1><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(gout, ids, n, L, gtable, R);
   R4R_CHECK_LAUNCH("rows_scatter_add");
   return 0;
 }
