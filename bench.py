@@ -358,7 +358,12 @@ def run_b200(args):
     se_sum = torch.zeros(1, device=dev, dtype=torch.float32)
     conv_events = []
     ops.set_conv_event_sink(conv_events)
-    steps_res = [CapturedStep(model, criterion, opt, d, y, se_sum, group, float(world)) for d, y in res_batches]
+    # sharded word table: every step's graph also carries the NEXT step's word lookup on a forked branch (the table is
+    # frozen, the lookup depends on token ids only), so the all-to-all latency hides behind this step's conv
+    prefetch = (world > 1 or args.force_shard) and not is_tn and args.table == "sharded" and not args.no_prefetch
+    steps_res = [CapturedStep(model, criterion, opt, d, y, se_sum, group, float(world),
+                              next_data=res_batches[(bi + 1) % pool_n][0] if prefetch else None)
+                 for bi, (d, y) in enumerate(res_batches)]
     launches_per_step = steps_res[0].launches              # this library's kernels inside one captured step
     res_events = list(conv_events)
     ops.set_conv_event_sink(None)
@@ -375,6 +380,7 @@ def run_b200(args):
         return [float(x) for x in t.tolist()]
 
     # ---- value: device-resident inputs
+    steps_res[0].prime()
     for i in range(W):
         steps_res[i % pool_n].replay()
     barrier()
@@ -408,17 +414,23 @@ def run_b200(args):
     # read back D2H every step.
     main = torch.cuda.current_stream()
     se_e2e = torch.zeros(1, device=dev, dtype=torch.float32)
-    steps_e2e = []
-    for s_ in range(2):
+    n_slots = 3 if prefetch else 2
+    if prefetch:
+        rr = RaggedReader(hp, arrays, dev, slots=3, native=True)
+    staged = []
+    for s_ in range(n_slots):
         d_, y_, _ = rr.stage(s_, s_)
         rr.wait_ready(s_, main)
-        torch.cuda.synchronize()
-        steps_e2e.append(CapturedStep(model, criterion, opt, d_, y_, se_e2e, group, float(world)))
+        staged.append((d_, y_))
+    torch.cuda.synchronize()
+    steps_e2e = [CapturedStep(model, criterion, opt, d_, y_, se_e2e, group, float(world),
+                              next_data=staged[(s_ + 1) % n_slots][0] if prefetch else None) for s_, (d_, y_) in enumerate(staged)]
+    for s_ in range(n_slots):
         rr.release(s_, main)
     se_host = torch.zeros(max(K, W), dtype=torch.float32).pin_memory()
     h2d_log = []
 
-    def e2e_loop(n):
+    def e2e_loop_pair(n):
         for i in range(n):
             s_ = i & 1
             rr.stage(i % pool_n, s_)                              # H2D of the ragged batch, on the copy stream
@@ -427,6 +439,26 @@ def run_b200(args):
             steps_e2e[s_].replay()
             rr.release(s_, main)
             se_host[i:i + 1].copy_(se_e2e, non_blocking=True)     # running SE sum, read back every step (main.py:57)
+
+    def e2e_loop_prefetch(n):
+        # three slots: step i computes on slot i % 3 (rows fetched by step i-1's forked branch) and looks up the batch
+        # in slot (i+1) % 3, whose H2D overlapped step i-1; the H2D of batch i+2 overlaps this step
+        rr.stage(0, 0)
+        h2d_log.append(rr.h2d_bytes_last)
+        rr.wait_ready(0, main)
+        steps_e2e[0].prime()                                      # the run's first batch has no predecessor
+        rr.stage(1 % pool_n, 1)
+        h2d_log.append(rr.h2d_bytes_last)
+        for i in range(n):
+            s_ = i % 3
+            rr.wait_ready((s_ + 1) % 3, main)                     # batch i+1 has landed
+            rr.stage((i + 2) % pool_n, (s_ + 2) % 3)              # waits (copy stream) for step i-1's release of that slot
+            h2d_log.append(rr.h2d_bytes_last)
+            steps_e2e[s_].replay()
+            rr.release(s_, main)
+            se_host[i:i + 1].copy_(se_e2e, non_blocking=True)
+
+    e2e_loop = e2e_loop_prefetch if prefetch else e2e_loop_pair
 
     def timed(loop, n):
         loop(min(W, n))
@@ -624,6 +656,7 @@ def main():
     ap.add_argument("--table", default="sharded", choices=["sharded", "replicated"], help="word table placement for --gpus > 1")
     ap.add_argument("--force-shard", action="store_true", help="run the sharded-table path at world size 1 (measures its device-side cost)")
     ap.add_argument("--transport", default="nccl", choices=["nccl", "p2p"], help="how sharded word rows travel")
+    ap.add_argument("--no-prefetch", action="store_true", help="sharded word table: look rows up inside the step that uses them (round-1 behaviour)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define R4R_ABI_VERSION 3
+#define R4R_ABI_VERSION 4
 
 #define R4R_EINVAL   (-1)   /* bad argument (null pointer, size out of supported range)          */
 #define R4R_EUNSUP   (-2)   /* shape outside what the sm_100a kernels were built for             */
@@ -123,6 +123,10 @@ int r4r_conv_wgrad_argmax_h_ragged(const void* shadow, int64_t V, int Epad, int 
                                    const int64_t* offsets, int64_t pad_id, int64_t N, int T, const int32_t* argmax,
                                    const float* pooled, const float* gpooled, int F, float* dW, float* db, void* stream);
 
+/* Number of persistent CTA pairs later r4r_conv_pool_tc launches use (0 = one per SM pair = all SMs).  Fewer pairs
+ * leave SMs to kernels of a concurrent stream / graph branch (the prefetched sharded word lookup). */
+int r4r_conv_set_clusters(int n);
+
 /* Diagnostics: when `buf32_u64` (device, 32 x uint64) is non-NULL every later r4r_conv_pool_tc launch
  * writes the per-role cycle counters of its first CTA pair there (see conv_tc.cu); NULL turns it off. */
 int r4r_conv_debug_profile(void* buf32_u64);
@@ -201,11 +205,11 @@ int r4r_counter_inc(int32_t* counter, void* stream);
  * same nn.Embedding / Tensor.gather call sites as r4r_word_gather_f32 / r4r_rows_gather.
  * Request message (int64 words): for every peer q a block of 1+cap words: [n_q, local_row_0 .. ].
  * Row payloads are [q][cap][row_bytes]; request (q, j) comes back at slot q*cap + j. */
-/* flags[idx[i]] = 1 (int32 flags[V], zero before the first call of a step) */
+/* sets bit idx[i] of the presence bitmap flags[] (>= ceil(V/32) 32-bit words, all zero before the first call of a step) */
 int r4r_shard_mark(const int64_t* idx, int64_t n, int64_t V, int32_t* flags, void* stream);
-/* compacts the flagged ids per owner in increasing id order into req[P][1+cap], writes
- * slot[id] = owner*cap + position (or -1), and clears flags.  cap >= ceil(V/P). */
-int r4r_shard_plan(int32_t* flags, int64_t V, int P, int64_t cap, int64_t* req, int64_t* slot, void* stream);
+/* appends every flagged id to the request block of its owner (req[id % P] gets the owner-local row id / P; the
+ * order inside a block is unspecified -- rows are placed back by id) and clears flags.  cap >= ceil(V/P). */
+int r4r_shard_plan(int32_t* flags, int64_t V, int P, int64_t cap, int64_t* req, void* stream);
 /* id tables: no de-duplication; pos[i] = slot of ids[i]; req is zeroed inside.  cap >= n. */
 int r4r_shard_bucket(const int64_t* ids, int64_t n, int64_t R, int P, int64_t cap, int64_t* req, int64_t* pos,
                      void* stream);
@@ -216,8 +220,11 @@ int r4r_shard_serve(const void* shard, int64_t rows_local, int row_bytes, const 
  * out_ptrs_host[q] -- rank q's receive buffer (+ this rank's block offset) mapped over NVLink. */
 int r4r_shard_serve_p2p(const void* shard, int64_t rows_local, int row_bytes, const int64_t* rreq, int P, int64_t cap,
                         void* const* out_ptrs_host, void* stream);
-/* out[i] = slot[idx[i]]  (token ids -> rows of the per-step row cache) */
-int r4r_shard_remap(const int64_t* idx, int64_t n, const int64_t* slot, int64_t V, int64_t* out, void* stream);
+/* requester side of a word lookup: rows [P][cap][row_bytes] came back compact; cache[req[q][1+j]*P + q] = rows[q][j],
+ * i.e. the per-step row cache [V (+1 zero row), row_bytes] is indexed by the ORIGINAL token id and the conv / wgrad
+ * kernels read their usual token ids (nn.Embedding semantics over the full table, DeepCoNN.py:53-54). */
+int r4r_shard_place(const void* rows, const int64_t* req, int P, int64_t cap, int row_bytes, void* cache, int64_t V,
+                    void* stream);
 /* owner side of the backward: gtable[rreq(q, j)][:] += scale * grads[q*cap + j][:] for j < n_q */
 int r4r_shard_scatter_add(const float* grads, const int64_t* rreq, int P, int64_t cap, int L, float* gtable,
                           int64_t rows_local, float scale, void* stream);

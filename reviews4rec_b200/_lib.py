@@ -39,6 +39,7 @@ SIGNATURES = {
     "r4r_doc_plan_ragged": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
     "r4r_conv_wgrad_argmax_h_ragged": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
     "r4r_conv_debug_profile": (c_int, [c_vp]),
+    "r4r_conv_set_clusters": (c_int, [c_int]),
     "r4r_conv_wgrad_argmax": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
     "r4r_conv_wgrad_argmax_h": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
     "r4r_conv_dgrad_scatter": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_i64, c_vp]),
@@ -54,11 +55,11 @@ SIGNATURES = {
     "r4r_adam_step": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp] + [c_f32] * 5 + [c_vp]),
     "r4r_counter_inc": (c_int, [c_vp, c_vp]),
     "r4r_shard_mark": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp]),
-    "r4r_shard_plan": (c_int, [c_vp, c_i64, c_int, c_i64, c_vp, c_vp, c_vp]),
+    "r4r_shard_plan": (c_int, [c_vp, c_i64, c_int, c_i64, c_vp, c_vp]),
     "r4r_shard_bucket": (c_int, [c_vp, c_i64, c_i64, c_int, c_i64, c_vp, c_vp, c_vp]),
     "r4r_shard_serve": (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_i64, c_vp, c_vp]),
     "r4r_shard_serve_p2p": (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_i64, c_vp, c_vp]),
-    "r4r_shard_remap": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
+    "r4r_shard_place": (c_int, [c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_i64, c_vp]),
     "r4r_shard_scatter_add": (c_int, [c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_i64, c_f32, c_vp]),
 }
 
@@ -68,14 +69,14 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn.argtypes = _args
 
 R4R_DT_F16, R4R_DT_BF16 = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 if lib.r4r_abi_version() != ABI_VERSION:
     raise ImportError("reviews4rec_b200: libr4r_b200.so ABI %d != expected %d -- rebuild" % (lib.r4r_abi_version(), ABI_VERSION))
 
 # number of kernel launches issued through this binding (bench.py reports it as gpu_launches)
 launch_count = 0
-_LAUNCHES_PER_CALL = {"r4r_conv_pool_simt": 2, "r4r_linear_bwd": 2, "r4r_shard_bucket": 2, "r4r_doc_plan": 3, "r4r_doc_plan_ragged": 3}
+_LAUNCHES_PER_CALL = {"r4r_conv_pool_simt": 2, "r4r_linear_bwd": 2, "r4r_shard_bucket": 2, "r4r_shard_plan": 2, "r4r_doc_plan": 3, "r4r_doc_plan_ragged": 3}
 
 
 def check(rc, name="r4r"):

@@ -714,6 +714,15 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
 }
 }  // namespace
 
+static int g_clusters = 0;
+// Persistent CTA pairs the next r4r_conv_pool_tc launches use (0 = one per SM pair).  The kernel owns every SM it
+// runs on (one CTA with all of the shared memory), so kernels of a concurrent stream / graph branch -- the sharded
+// word lookup of the next step and its NCCL all-to-alls (train.CapturedStep) -- only overlap if some pairs stay free.
+extern "C" int r4r_conv_set_clusters(int n) {
+  g_clusters = n > 0 ? n : 0;
+  return 0;
+}
+
 static unsigned long long* g_prof = nullptr;
 // Diagnostics: 32 x uint64 device buffer receiving the per-role cycle counters of cluster 0
 // ([rank*16+0..3] epilogue total / wait tmem_full / bar.sync / exchange, [rank*16+4..6] producer
@@ -808,6 +817,12 @@ static int conv_pool_tc_launch(const void* shadow, int64_t V, int Epad, int E, i
 
   R4R_CUDA(cudaFuncSetAttribute(conv_pool_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   long long nclusters = sm_count / 2;
+  {
+    int want = g_clusters;                                  // r4r_conv_set_clusters: leave SM pairs free for a concurrent graph branch
+    const char* e = getenv("R4R_CONV_CLUSTERS");            // tuning override
+    if (e && atoi(e) >= 1) want = atoi(e);
+    if (want >= 1 && want < nclusters) nclusters = want;
+  }
   if (nclusters > N) nclusters = N;
   conv_pool_tc_kernel<<<(unsigned)(2 * nclusters), NUM_THREADS, smem_bytes, as_stream(stream)>>>(P);
   R4R_CHECK_LAUNCH("conv_pool_tc");

@@ -5,7 +5,9 @@
 // (DeepCoNN.py:53-54,70-71, NARRE.py:87-88,110-116, TransNet.py:108-109, MF.py:45-46,52-53) when row
 // r of the table lives on rank r % P at local row r / P.
 //
-// A lookup is   plan -> [ids out] -> serve -> [rows back] -> remap/gather   where the two bracketed
+// A word lookup is   mark -> plan -> [ids out] -> serve -> [rows back] -> place   (the rows land in a per-step
+// cache indexed by the ORIGINAL token id, so the conv / wgrad kernels read their usual ids: no remapped id
+// tensors); an id-table lookup is   bucket -> [ids out] -> serve -> [rows back] -> gather.   The two bracketed
 // steps are either NCCL all-to-alls (equal splits, CUDA-graph capturable) or -- fused variant --
 // r4r_shard_serve_p2p, which gathers the requested rows and stores them straight into the
 // requesters' receive buffers over NVLink peer mappings.
@@ -20,21 +22,17 @@
 namespace {
 constexpr int THREADS = 256;
 
-// ---- word-table plan, step 1: presence flags of the token ids of this rank's documents.
-// Padding makes ~60 % of all tokens the SAME id and the rest is Zipfian, so marking flags[id]
-// directly would queue millions of accesses on a handful of L2 sectors (each SM keeps a stale 0 in
-// its L1).  Every CTA therefore collects the ids it sees in a shared-memory bitmap first (ids below
-// MARK_BITS; a lane also skips an id equal to its left neighbour's or to the one it handled last) and
-// publishes the set bits once at the end: at most one global access per (CTA, distinct id).
+// ---- word-table plan, step 1: presence BITMAP (bit id of flags[], 32 ids per word) of the token ids of this
+// rank's documents.  Padding makes ~60 % of all tokens the SAME id and the rest is Zipfian, so setting global
+// bits directly would queue millions of accesses on a handful of L2 sectors.  Every CTA therefore collects the
+// ids it sees in a shared-memory bitmap first (ids below MARK_BITS; a lane also skips an id equal to its left
+// neighbour's or to the one it handled last) and ORs its non-zero words into the global bitmap once at the end:
+// at most one fire-and-forget reduction per (CTA, 32-id word).
 constexpr int MARK_THREADS = 512;
 constexpr int64_t MARK_BITS = 1 << 20;               // 128 KB of shared memory covers ids < 1,048,576
 
-__device__ __forceinline__ void mark_global(int32_t* flags, int64_t id) {
-  if (__ldcg(flags + id) == 0) flags[id] = 1;        // benign race: every writer stores 1
-}
-
 __global__ void __launch_bounds__(MARK_THREADS) shard_mark_kernel(const int64_t* __restrict__ idx, int64_t n, int64_t V,
-                                                                  int32_t* __restrict__ flags, int64_t bits) {
+                                                                  uint32_t* __restrict__ flags, int64_t bits) {
   extern __shared__ uint32_t bitmap[];               // bits / 32 words
   const int words = (int)((bits + 31) >> 5);
   for (int w = threadIdx.x; w < words; w += MARK_THREADS) bitmap[w] = 0u;
@@ -57,65 +55,52 @@ __global__ void __launch_bounds__(MARK_THREADS) shard_mark_kernel(const int64_t*
       const int64_t left = __shfl_up_sync(0xffffffffu, id[u], 1);
       if (id[u] >= 0 && id[u] != mine && (lane == 0 || id[u] != left)) {
         mine = id[u];
+        const uint32_t m = 1u << (id[u] & 31);
         if (id[u] < bits) {
-          const uint32_t m = 1u << (id[u] & 31);
           if ((bitmap[id[u] >> 5] & m) == 0u) atomicOr(&bitmap[id[u] >> 5], m);
         } else {
-          mark_global(flags, id[u]);                   // beyond the bitmap: rare ids of a very large vocabulary
+          atomicOr(flags + (id[u] >> 5), m);           // beyond the shared bitmap: rare ids of a very large vocabulary
         }
       }
     }
   }
   __syncthreads();
   for (int w = threadIdx.x; w < words; w += MARK_THREADS) {
-    uint32_t b = bitmap[w];
-    while (b) {
-      const int k = __ffs(b) - 1;
-      b &= b - 1;
-      mark_global(flags, (int64_t)w * 32 + k);
-    }
+    const uint32_t b = bitmap[w];
+    if (b) atomicOr(flags + w, b);
   }
 }
 
-// ---- word-table plan, step 2: CTA o compacts the flagged rows owned by rank o (ids o, o+P, ...)
-// into its request block, in increasing id order (deterministic), and records each id's slot.
-constexpr int PLAN_THREADS = 1024;
-__global__ void __launch_bounds__(PLAN_THREADS) shard_plan_kernel(int32_t* __restrict__ flags, int64_t V, int P, int64_t cap,
-                                                                  int64_t* __restrict__ req, int64_t* __restrict__ slot) {
-  __shared__ int warp_tot[PLAN_THREADS / 32];
-  __shared__ int chunk_base;
-  const int o = blockIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t rows = (V - o + P - 1) / P;            // rows owned by rank o
-  int64_t* block = req + (int64_t)o * (1 + cap);
-  if (threadIdx.x == 0) chunk_base = 0;
-  __syncthreads();
-  for (int64_t l0 = 0; l0 < rows; l0 += PLAN_THREADS) {
-    const int64_t l = l0 + threadIdx.x;
-    const int64_t id = l * P + o;
-    const bool on = l < rows && flags[id] != 0;
-    const unsigned ballot = __ballot_sync(0xffffffffu, on);
-    const int before = __popc(ballot & ((1u << lane) - 1u));
-    if (lane == 0) warp_tot[warp] = __popc(ballot);
-    __syncthreads();
-    int wbase = 0;
-    for (int w = 0; w < warp; ++w) wbase += warp_tot[w];
-    const int base = chunk_base;
-    if (l < rows) {
-      if (on) {
-        const int64_t p = base + wbase + before;
-        block[1 + p] = l;
-        slot[id] = (int64_t)o * cap + p;
-        flags[id] = 0;                                // leave the flag array clean for the next step
-      } else {
-        slot[id] = -1;
-      }
+// ---- word-table plan, step 2: every flagged id goes into the request block of its owner (id % P) as the
+// owner-local row id / P.  The order inside a block is irrelevant -- the rows are placed back by id
+// (shard_place_kernel) -- so the compaction is a warp-aggregated atomic append, spread over the whole grid.
+__global__ void __launch_bounds__(32) shard_plan_zero_kernel(int64_t* __restrict__ req, int P, int64_t cap) {
+  if ((int)threadIdx.x < P) req[(int64_t)threadIdx.x * (1 + cap)] = 0;
+}
+
+__global__ void __launch_bounds__(THREADS) shard_plan_kernel(uint32_t* __restrict__ flags, int64_t V, int P, int64_t cap,
+                                                             int64_t* __restrict__ req) {
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * THREADS;
+  for (int64_t i0 = (int64_t)blockIdx.x * THREADS + (threadIdx.x & ~31); i0 < V; i0 += stride) {   // one bitmap word per warp trip
+    const int64_t id = i0 + lane;
+    const uint32_t word = flags[i0 >> 5];
+    const bool on = id < V && ((word >> lane) & 1u);
+    __syncwarp();
+    if (lane == 0 && word) flags[i0 >> 5] = 0u;         // leave the bitmap clean for the next step
+    const int o = on ? (int)(id % P) : -1 - lane;       // distinct negatives never match
+    const unsigned grp = __match_any_sync(0xffffffffu, o);
+    if (on) {
+      const int leader = __ffs(grp) - 1;
+      unsigned long long base = 0;
+      int64_t* block = req + (int64_t)o * (1 + cap);
+      if (lane == leader) base = atomicAdd(reinterpret_cast<unsigned long long*>(block), (unsigned long long)__popc(grp));
+      base = __shfl_sync(grp, base, leader);
+      const int64_t p = (int64_t)base + __popc(grp & ((1u << lane) - 1u));
+      if (p >= cap) __trap();
+      block[1 + p] = id / P;
     }
-    __syncthreads();
-    if (threadIdx.x == PLAN_THREADS - 1) chunk_base = base + wbase + __popc(ballot);
-    __syncthreads();
   }
-  if (threadIdx.x == 0) block[0] = chunk_base;
 }
 
 // ---- id-table plan: no de-duplication (n is a few rows per rating); pos[i] = slot of ids[i]
@@ -170,14 +155,28 @@ __global__ void __launch_bounds__(THREADS) shard_serve_kernel(const uint8_t* __r
   }
 }
 
-__global__ void __launch_bounds__(THREADS) shard_remap_kernel(const int64_t* __restrict__ idx, int64_t n, const int64_t* __restrict__ slot,
-                                                              int64_t V, int64_t* __restrict__ out) {
-  for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS) {
-    const int64_t id = __ldg(idx + i);
+// ---- requester side: the rows came back compact ([q][j] = the j-th row asked of owner q); copy each to
+// cache[id] with id = req[q][1+j] * P + q, so the cache is indexed by the original token id.
+template <bool VEC16>
+__global__ void __launch_bounds__(THREADS) shard_place_kernel(const uint8_t* __restrict__ rows, const int64_t* __restrict__ req, int P,
+                                                              int64_t cap, int row_bytes, uint8_t* __restrict__ cache, int64_t V) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (THREADS / 32);
+  const int64_t total = (int64_t)P * cap;
+  for (int64_t w = (int64_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5); w < total; w += warps) {
+    const int q = (int)(w / cap);
+    const int64_t j = w - (int64_t)q * cap;
+    const int64_t* block = req + (int64_t)q * (1 + cap);
+    if (j >= __ldg(block)) continue;
+    const int64_t id = __ldg(block + 1 + j) * P + q;
     if (id < 0 || id >= V) __trap();
-    const int64_t s = __ldg(slot + id);
-    if (s < 0) __trap();                               // id was not part of the plan
-    out[i] = s;
+    const uint8_t* src = rows + w * (int64_t)row_bytes;
+    uint8_t* dst = cache + id * (int64_t)row_bytes;
+    if (VEC16) {
+      for (int c = lane; c < row_bytes / 16; c += 32) reinterpret_cast<uint4*>(dst)[c] = __ldg(reinterpret_cast<const uint4*>(src) + c);
+    } else {
+      for (int c = lane; c < row_bytes / 4; c += 32) reinterpret_cast<uint32_t*>(dst)[c] = __ldg(reinterpret_cast<const uint32_t*>(src) + c);
+    }
   }
 }
 
@@ -229,6 +228,7 @@ inline unsigned grid_of(int64_t items, int per_block, int cap_blocks = 148 * 8) 
 }  // namespace
 
 extern "C" int r4r_shard_mark(const int64_t* idx, int64_t n, int64_t V, int32_t* flags, void* stream) {
+  // flags: >= ceil(V/32) zeroed 32-bit words used as a bitmap (bit id % 32 of word id / 32)
   R4R_REQUIRE(idx && flags, R4R_EINVAL, "shard_mark: null pointer");
   R4R_REQUIRE(n >= 0 && V > 0, R4R_EINVAL, "shard_mark: bad sizes");
   if (n == 0) return 0;
@@ -240,20 +240,21 @@ extern "C" int r4r_shard_mark(const int64_t* idx, int64_t n, int64_t V, int32_t*
     attr_set = true;
   }
   // few, fat CTAs: every CTA publishes its own bitmap, so their number bounds the global flag traffic
-  int64_t blocks = cdiv64(n, MARK_THREADS * 16);
-  const int64_t cap_blocks = smem > 48 * 1024 ? 148 : 148 * 2;
+  int64_t blocks = cdiv64(n, MARK_THREADS * 8);
+  const int64_t cap_blocks = smem > 48 * 1024 ? 148 : 148 * 4;      // small bitmaps: four CTAs per SM keep more loads in flight
   if (blocks > cap_blocks) blocks = cap_blocks;
   if (blocks < 1) blocks = 1;
-  shard_mark_kernel<<<(unsigned)blocks, MARK_THREADS, smem, as_stream(stream)>>>(idx, n, V, flags, bits);
+  shard_mark_kernel<<<(unsigned)blocks, MARK_THREADS, smem, as_stream(stream)>>>(idx, n, V, reinterpret_cast<uint32_t*>(flags), bits);
   R4R_CHECK_LAUNCH("shard_mark");
   return 0;
 }
 
-extern "C" int r4r_shard_plan(int32_t* flags, int64_t V, int P, int64_t cap, int64_t* req, int64_t* slot, void* stream) {
-  R4R_REQUIRE(flags && req && slot, R4R_EINVAL, "shard_plan: null pointer");
+extern "C" int r4r_shard_plan(int32_t* flags, int64_t V, int P, int64_t cap, int64_t* req, void* stream) {
+  R4R_REQUIRE(flags && req, R4R_EINVAL, "shard_plan: null pointer");
   R4R_REQUIRE(V > 0 && P >= 1 && P <= 16 && cap >= (V + P - 1) / P, R4R_EINVAL,
               "shard_plan: need 1 <= P <= 16 and cap >= ceil(V/P) (V=%lld P=%d cap=%lld)", (long long)V, P, (long long)cap);
-  shard_plan_kernel<<<P, PLAN_THREADS, 0, as_stream(stream)>>>(flags, V, P, cap, req, slot);
+  shard_plan_zero_kernel<<<1, 32, 0, as_stream(stream)>>>(req, P, cap);
+  shard_plan_kernel<<<grid_of(V, THREADS, 148 * 2), THREADS, 0, as_stream(stream)>>>(reinterpret_cast<uint32_t*>(flags), V, P, cap, req);
   R4R_CHECK_LAUNCH("shard_plan");
   return 0;
 }
@@ -311,12 +312,15 @@ extern "C" int r4r_shard_serve_p2p(const void* shard, int64_t rows_local, int ro
   return serve_launch(shard, rows_local, row_bytes, rreq, P, cap, A, bits % 16 == 0, stream);
 }
 
-extern "C" int r4r_shard_remap(const int64_t* idx, int64_t n, const int64_t* slot, int64_t V, int64_t* out, void* stream) {
-  R4R_REQUIRE(idx && slot && out, R4R_EINVAL, "shard_remap: null pointer");
-  R4R_REQUIRE(n >= 0 && V > 0, R4R_EINVAL, "shard_remap: bad sizes");
-  if (n == 0) return 0;
-  shard_remap_kernel<<<grid_of(n, THREADS * 4), THREADS, 0, as_stream(stream)>>>(idx, n, slot, V, out);
-  R4R_CHECK_LAUNCH("shard_remap");
+extern "C" int r4r_shard_place(const void* rows, const int64_t* req, int P, int64_t cap, int row_bytes, void* cache, int64_t V,
+                               void* stream) {
+  R4R_REQUIRE(rows && req && cache, R4R_EINVAL, "shard_place: null pointer");
+  R4R_REQUIRE(P >= 1 && P <= 16 && cap > 0 && row_bytes > 0 && row_bytes % 4 == 0 && V > 0, R4R_EINVAL, "shard_place: bad sizes");
+  const bool v16 = row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(rows) | reinterpret_cast<uintptr_t>(cache)) % 16 == 0;
+  const unsigned grid = grid_of((int64_t)P * cap, THREADS / 32);
+  if (v16) shard_place_kernel<true><<<grid, THREADS, 0, as_stream(stream)>>>(static_cast<const uint8_t*>(rows), req, P, cap, row_bytes, static_cast<uint8_t*>(cache), V);
+  else shard_place_kernel<false><<<grid, THREADS, 0, as_stream(stream)>>>(static_cast<const uint8_t*>(rows), req, P, cap, row_bytes, static_cast<uint8_t*>(cache), V);
+  R4R_CHECK_LAUNCH("shard_place");
   return 0;
 }
 

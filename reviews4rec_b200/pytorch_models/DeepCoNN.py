@@ -32,11 +32,16 @@ class DeepCoNN(nn.Module):
         self.dropout = nn.Dropout(hyper_params["dropout"])
         self.relu = nn.ReLU()
 
+    def word_inputs(self, data):
+        """The token-id tensors ``forward`` hands to the word table, in order (a sharded table can look them up
+        a step ahead: train.CapturedStep(next_data=...))."""
+        first_dim = data[5].numel()                             # explicit widths: a rank's slice of a batch may be empty
+        return data[3].reshape(first_dim, data[3].shape[-1]), data[4].reshape(first_dim, data[4].shape[-1])
+
     def forward(self, data):
         _, _, _, user_reviews, item_reviews, user_id, item_id = data
         final_shape = tuple(user_id.shape)                      # [B] or [B,n] (ranking, eval.py:64-92)
-        first_dim = user_id.numel()
-        user_docs, item_docs = self.word2vec.many(user_reviews.reshape(first_dim, -1), item_reviews.reshape(first_dim, -1))
+        user_docs, item_docs = self.word2vec.many(*self.word_inputs(data))
         user = self.user_conv(user_docs)
         item = self.item_conv(item_docs)
         cat = torch.cat([user, item], dim=-1)

@@ -42,6 +42,12 @@ class NARRE(nn.Module):
         scores = scorer(torch.cat([x, other_x], dim=-1))[:, :, 0]
         return torch.sum(F.softmax(scores, dim=-1).unsqueeze(-1) * x, dim=1)
 
+    def word_inputs(self, data):
+        """The token-id tensors ``forward`` hands to the word table: every review is its own document [n*R, W]."""
+        n = data[5].numel()
+        ur, ir = data[3], data[4]
+        return ur.reshape(n * ur.shape[-2], ur.shape[-1]), ir.reshape(n * ir.shape[-2], ir.shape[-1])
+
     def forward(self, data):
         _, users_who_reviewed, reviewed_items, user_reviews, item_reviews, user_id, item_id = data
         final_shape = tuple(user_id.shape)
@@ -54,7 +60,7 @@ class NARRE(nn.Module):
         ub = ops.rows_gather(self.user_bias, user_id)
         ib = ops.rows_gather(self.item_bias, item_id)
         # every review is its own conv document: [n*R, W] token ids (NARRE.py:91-104)
-        user_docs, item_docs = self.word2vec.many(user_reviews.reshape(n * R_u, W_u), item_reviews.reshape(n * R_i, W_i))
+        user_docs, item_docs = self.word2vec.many(*self.word_inputs(data))
         user = self.user_conv(user_docs).view(n, R_u, -1)
         item = self.item_conv(item_docs).view(n, R_i, -1)
         user = self.attention(user, self.item_embedding(reviewed_items), self.attention_scorer_user)

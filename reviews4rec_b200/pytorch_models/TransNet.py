@@ -76,12 +76,16 @@ class TransNet(nn.Module):
             self.source_fm = TorchFM(L, 8)
         self.dropout = nn.Dropout(hyper_params["dropout"])
 
+    def word_inputs(self, data):
+        """The token-id tensors ``forward`` hands to the word table: user document, item document, this review."""
+        n = data[5].numel()
+        return tuple(data[j].reshape(n, data[j].shape[-1]) for j in (3, 4, 0))
+
     def forward(self, data):
         this_reviews, _, _, user_reviews, item_reviews, user_id, item_id = data
         final_shape = tuple(user_id.shape)
         n = user_id.numel()
-        user, item, this = self.target.word2vec.many(user_reviews.reshape(n, -1), item_reviews.reshape(n, -1),
-                                                     this_reviews.reshape(n, -1))
+        user, item, this = self.target.word2vec.many(*self.word_inputs(data))
         self.source(user, item)
         if self.hyper_params["model_type"] == "transnet++":
             u = self.dropout(self.user_embedding(user_id.reshape(-1)))

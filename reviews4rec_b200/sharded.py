@@ -10,7 +10,7 @@ here is "the same numbers as the single-process reference at the same global bat
   ids); the local shard has ``ceil(R / P)`` rows;
 * the frozen word table (DeepCoNN.py:15) is looked up forward-only: per step the rank de-duplicates the
   token ids of its documents, asks the owners for the rows and receives a compact per-step row cache that
-  the unchanged conv / wgrad kernels read through remapped ids;
+  the unchanged conv / wgrad kernels read through their ORIGINAL token ids (the cache is indexed by id);
 * the trainable id tables / bias vectors (``nn.Embedding(sparse=False)`` / ``Tensor.gather`` at
   MF.py:45-53, NARRE.py:87-88,110-116, TransNet.py:108-109, DeepCoNN.py:70-71) get rows back per id, send
   row gradients to the owners in the backward, and every local row is then updated by the dense Adam
@@ -75,8 +75,8 @@ class _DeviceKernels:
         call("r4r_shard_mark", _p(idx), idx.numel(), V, _p(flags), _stream())
 
     @staticmethod
-    def plan(flags, V, P, cap, req, slot):
-        call("r4r_shard_plan", _p(flags), V, P, cap, _p(req), _p(slot), _stream())
+    def plan(flags, V, P, cap, req):
+        call("r4r_shard_plan", _p(flags), V, P, cap, _p(req), _stream())
 
     @staticmethod
     def bucket(ids, R, P, cap, req, pos):
@@ -95,8 +95,9 @@ class _DeviceKernels:
              ctypes.cast(arr, ctypes.c_void_p), _stream())
 
     @staticmethod
-    def remap(idx, slot, out):
-        call("r4r_shard_remap", _p(idx), idx.numel(), _p(slot), slot.numel(), _p(out), _stream())
+    def place(rows, req, P, cap, cache, V):
+        row_bytes = (cache.numel() // cache.shape[0]) * cache.element_size()
+        call("r4r_shard_place", _p(rows), _p(req), P, cap, row_bytes, _p(cache), V, _stream())
 
     @staticmethod
     def gather(table, pos, out):
@@ -141,15 +142,13 @@ class Transport:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
         return int(t.item())
 
-    def exchange_rows(self, shard, rreq, P, cap, row_shape, dtype, zero_row=False):
+    def exchange_rows(self, shard, rreq, P, cap, row_shape, dtype):
         """Owner side of a lookup + the rows' way back: returns the [P * cap, *row_shape] rows this rank
-        asked for (slot order); ``zero_row`` appends one all-zero row (the conv's padding row)."""
+        asked for, compact: block q holds the rows requested of owner q in request order."""
         payload = torch.empty((P, cap) + tuple(row_shape), device=shard.device, dtype=dtype)
         K.serve(shard, rreq, P, cap, payload)
-        out = torch.empty((P * cap + (1 if zero_row else 0),) + tuple(row_shape), device=shard.device, dtype=dtype)
-        if zero_row:
-            out[P * cap:].zero_()
-        self.all_to_all(out[: P * cap], payload)
+        out = torch.empty((P * cap,) + tuple(row_shape), device=shard.device, dtype=dtype)
+        self.all_to_all(out, payload)
         return out
 
 
@@ -175,7 +174,7 @@ class P2PTransport(Transport):
         epad = ((E + 63) // 64) * 64
         return cls(group, max_block_bytes=rows_local(V, world) * max(E * 4, epad * 2))
 
-    def exchange_rows(self, shard, rreq, P, cap, row_shape, dtype, zero_row=False):
+    def exchange_rows(self, shard, rreq, P, cap, row_shape, dtype):
         n_row = 1
         for d in row_shape:
             n_row *= d
@@ -186,12 +185,10 @@ class P2PTransport(Transport):
         self.hdl.barrier(channel=0)                      # every rank has consumed the previous contents of its buffer
         ptrs = [self.peer_ptrs[q] + self.rank * block for q in range(P)]
         K.serve_p2p(shard, rreq, P, cap, ptrs)
-        if zero_row:
-            self.buf[P * block: P * block + row_bytes].zero_()
         self.hdl.barrier(channel=1)                      # all peers' stores into my buffer have landed
         # valid until this rank's NEXT exchange_rows: peers only write after the channel-0 barrier of that call,
         # i.e. after this rank's stream has finished everything queued before it (one lookup per step)
-        rows = P * cap + (1 if zero_row else 0)
+        rows = P * cap
         return self.buf[: rows * row_bytes].view(dtype).view((rows,) + tuple(row_shape))
 
 
@@ -210,46 +207,90 @@ class ShardedWordTable(nn.Module):
         self.weight = nn.Parameter(shard_rows(full_weight.detach().float(), rank, P).contiguous(), requires_grad=False)
         self.requires_grad = False                      # the inert attribute the reference sets (DeepCoNN.py:16)
         self._scr = None
+        self._slots = {}
         from . import ops
         self._own_shadow = ops.ShadowTable()
 
     def _scratch(self, dev):
         if self._scr is None or self._scr[0].device != dev:
             flags = torch.zeros(self.V, device=dev, dtype=torch.int32)
-            slot = torch.empty(self.V, device=dev, dtype=torch.int64)
             req = torch.zeros(self.P, 1 + self.cap, device=dev, dtype=torch.int64)
             rreq = torch.zeros_like(req)
-            self._scr = (flags, slot, req, rreq)
+            self._scr = (flags, req, rreq)
         return self._scr
 
+    @staticmethod
+    def _key(idx_list):
+        from . import ops
+        return tuple(((i.tokens.data_ptr(), i.offsets.data_ptr()) if isinstance(i, ops.RaggedIdx) else (i.data_ptr(), 0)) + tuple(i.shape)
+                     for i in idx_list)
+
+    def _new_cache(self, mode):
+        """Row cache indexed by the ORIGINAL token id: [V, E] fp32 (exact mode) or [V + 1, Epad] half rows with the
+        conv kernel's all-zero padding row at V.  Only the rows of the current step's tokens are valid."""
+        dev = self.weight.device
+        if mode == "exact":
+            return torch.empty(self.V, self.E, device=dev, dtype=torch.float32)
+        own = self._own_shadow.get(self.weight, mode)
+        cache = torch.empty(self.V + 1, own.shape[1], device=dev, dtype=own.dtype)
+        cache[self.V:].zero_()
+        return cache
+
+    def reserve(self, *idx_list):
+        """A persistent row cache for the lookup of these index tensors -- the static input buffers of a captured
+        step.  ``fill`` writes it, ``many`` on the same tensors returns it without exchanging: the lookup of step
+        k+1 can then run on a side stream / graph branch while step k computes, which the frozen table permits
+        (the lookup depends on the batch's token ids only)."""
+        from . import ops
+        key = self._key(idx_list)
+        slot = self._slots.get(key)
+        if slot is None:
+            mode = ops.get_conv_mode()
+            slot = self._slots[key] = {"mode": mode, "rows": self._new_cache(mode), "filled": False, "executed": False, "docs": None}
+        return slot
+
+    def fill(self, slot, *idx_list):
+        """Run the exchange for ``idx_list`` into a reserved slot (current stream; graph-capturable)."""
+        slot["docs"] = self._lookup(idx_list, slot)
+        slot["filled"] = True
+        if not torch.cuda.is_current_stream_capturing():
+            slot["executed"] = True                     # a captured fill only runs when its graph is replayed
+
     def many(self, *idx_list):
+        slot = self._slots.get(self._key(idx_list)) if self._slots else None
+        if slot is not None and slot["filled"]:
+            from . import ops
+            if slot["mode"] != ops.get_conv_mode():
+                raise RuntimeError("prefetched word rows were fetched for conv mode %r" % slot["mode"])
+            return slot["docs"]
+        return self._lookup(idx_list, None)
+
+    def _lookup(self, idx_list, into):
         from . import ops
         from .pytorch_models.common_pytorch_models import Docs
         dev = self.weight.device
-        flags, slot, req, rreq = self._scratch(dev)
-        # ragged documents are expanded first (the sharded lookup marks / remaps padded id tensors)
+        flags, req, rreq = self._scratch(dev)
+        # ragged documents are expanded first (the sharded lookup marks padded id tensors)
         idx_list = [(i.padded() if isinstance(i, ops.RaggedIdx) else i).contiguous() for i in idx_list]
         for idx in idx_list:
             K.mark(idx, self.V, flags)
-        K.plan(flags, self.V, self.P, self.cap, req, slot)
+        K.plan(flags, self.V, self.P, self.cap, req)
         self.transport.all_to_all(rreq, req)
         mode = ops.get_conv_mode()
+        cache = into["rows"] if into else self._new_cache(mode)
         if mode == "exact":
             # strict-parity mode: fp32 rows, the conv / wgrad kernels read the cache as their word table
-            table = self.transport.exchange_rows(self.weight, rreq, self.P, self.cap, (self.E,), torch.float32)
-            shadow = None
+            rows = self.transport.exchange_rows(self.weight, rreq, self.P, self.cap, (self.E,), torch.float32)
+            K.place(rows, req, self.P, self.cap, cache, self.V)
+            table, shadow = cache, None
         else:
             # tensor-core modes: the owner serves rows of its half-precision shadow shard (built once: the
             # table is frozen), already in the conv kernel's layout -> half the NVLink bytes, no conversion
             own = self._own_shadow.get(self.weight, mode)
-            rows = self.transport.exchange_rows(own, rreq, self.P, self.cap, (own.shape[1],), own.dtype, zero_row=True)
-            table, shadow = None, ops.PrebuiltShadow(rows, self.P * self.cap, self.E, mode)
-        out = []
-        for idx in idx_list:
-            ridx = torch.empty_like(idx)
-            K.remap(idx, slot, ridx)
-            out.append(Docs(ridx, table, shadow))
-        return tuple(out)
+            rows = self.transport.exchange_rows(own, rreq, self.P, self.cap, (own.shape[1],), own.dtype)
+            K.place(rows, req, self.P, self.cap, cache, self.V)
+            table, shadow = None, ops.PrebuiltShadow(cache, self.V, self.E, mode)
+        return tuple(Docs(idx, table, shadow) for idx in idx_list)
 
     def forward(self, idx):
         return self.many(idx)[0]

@@ -9,6 +9,8 @@ torch >= 1.5 in the reference (in-place optimizer step between ``backward(retain
 calls), is the exact restatement: three ``autograd.grad`` calls on one graph, then the three
 optimizer steps in the reference's order (target, source, source_fm).
 """
+import os
+
 import torch
 
 TRANSNET = ("transnet", "transnet++")
@@ -140,7 +142,11 @@ class CapturedStep:
     The optimizer must be graph-safe: ``FusedAdam(capturable=True)``.
     """
 
-    def __init__(self, model, criterion, optimizer, data, y, se_sum=None, group=None, grad_div=1.0):
+    def __init__(self, model, criterion, optimizer, data, y, se_sum=None, group=None, grad_div=1.0, next_data=None):
+        """``next_data``: the static input buffers of the step that will be replayed AFTER this one.  With a
+        row-sharded word table the graph then carries that step's word lookup (mark / plan / all-to-all / serve /
+        all-to-all / place) on a forked branch next to this step's compute, and this step reads the rows its
+        predecessor fetched: the table is frozen, so a lookup depends on the batch's token ids only."""
         self.model, self.data, self.y = model, data, y
         dev = y.device
         self.se_sum = se_sum if se_sum is not None else torch.zeros(1, device=dev, dtype=torch.float32)
@@ -149,14 +155,34 @@ class CapturedStep:
         for o in (optimizer if isinstance(optimizer, (list, tuple)) else [optimizer]):
             if hasattr(o, "prepare"):
                 o.prepare()
+        words = None
+        if next_data is not None and hasattr(model, "word_inputs"):
+            from .sharded import ShardedWordTable
+            words = next((m for m in model.modules() if isinstance(m, ShardedWordTable)), None)
+        if words is not None:
+            cur_idx, nxt_idx = model.word_inputs(data), model.word_inputs(next_data)
+            cur_slot, nxt_slot = words.reserve(*cur_idx), words.reserve(*nxt_idx)
+            if not cur_slot["executed"]:
+                words.fill(cur_slot, *cur_idx)          # rows for the eager pass below (a predecessor's fill is only captured so far)
+            self._prime = lambda: words.fill(cur_slot, *cur_idx)
         with torch.no_grad():
             model(data)             # eager pass: builds the shadow word table and lazy kernel attributes outside the graph
         model.zero_grad(set_to_none=True)
+        side = torch.cuda.Stream(device=dev) if words is not None else None
         self.graph = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
         from . import _lib, ops
         launches0 = _lib.launch_count
+        if words is not None:
+            # the conv kernel owns every SM it runs on; leave 4 of the 74 SM pairs to the forked lookup branch and its
+            # NCCL kernels (measured at 2 x B200: 1.335 -> 1.271 ms per step; 72 and <= 66 pairs are slower)
+            _lib.lib.r4r_conv_set_clusters(int(os.environ.get("R4R_PREFETCH_CLUSTERS", "70")))
         with torch.cuda.graph(self.graph):
+            if words is not None:                   # forked branch: the NEXT step's word lookup
+                cur = torch.cuda.current_stream()
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    words.fill(nxt_slot, *nxt_idx)
             ops.arena_begin(dev)                    # one memset for all the zeroed gradient buffers of the step
             if is_tn:
                 if group is not None:
@@ -176,8 +202,18 @@ class CapturedStep:
                     allreduce_dense_grads(model, group, int(grad_div))
                 optimizer.step()
             ops.arena_end()
+            if words is not None:
+                torch.cuda.current_stream().wait_stream(side)
+        if words is not None:
+            _lib.lib.r4r_conv_set_clusters(0)
         self.launches = _lib.launch_count - launches0       # kernels of this library one replay launches
         self.out = out
+
+    def prime(self):
+        """Fetch this step's word rows now (eagerly): needed once before the first replay of a run whose steps
+        prefetch each other's rows, and whenever the static input buffers were refilled behind the graphs' back."""
+        if getattr(self, "_prime", None) is not None:
+            self._prime()
 
     def replay(self):
         self.graph.replay()

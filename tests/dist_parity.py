@@ -88,11 +88,67 @@ def main():
                 assert_close(sd[k], ref[k], rtol=1e-4, atol=atol, msg="%s final.%s" % (mt, k))
             print("dist_parity[%s, %s, %s, world %d]: MSE %.6f (reference %.6f), %d tensors match" % (mt, mode, args.transport, world, mse, want, len(ref) if mode == "exact" else 0), flush=True)
         dist.barrier()
+    captured_prefetch_check(rank, world, tr)
     if rank == 0:
         print("DIST_PARITY_OK", flush=True)
     torch.cuda.synchronize()
     sys.stdout.flush()
     os._exit(0)                                              # skip NCCL / symmetric-memory teardown
+
+
+def captured_prefetch_check(rank, world, tr):
+    """train.CapturedStep with the word lookup of step k+1 prefetched on a forked graph branch (next_data=...) must
+    train exactly like the eager sharded loop on the same ranks: 8-rating global batches split evenly, two epochs."""
+    import reviews4rec_b200 as R
+    from reviews4rec_b200 import sharded as S
+    from reviews4rec_b200.optim import FusedAdam
+    from reviews4rec_b200.train import CapturedStep
+    from tests.helpers import assert_close, golden_batches, load_golden
+    from tests.test_gpu_models import build
+    for mt, mode in (("deepconn", "exact"), ("deepconn++", "f16"), ("NARRE", "f16")):
+        z, dims = load_golden(mt)
+        gb = golden_batches(z, dims, "cuda")
+        cat = lambda a, b: None if a is None else torch.cat([a, b[:3]])
+        big = [([cat(d0, d1) for d0, d1 in zip(gb[i][0], gb[(i + 1) % len(gb)][0])], torch.cat([gb[i][1], gb[(i + 1) % len(gb)][1][:3]]))
+               for i in range(len(gb))]                         # 8 ratings per global batch
+        local = [S.shard_batch(d, y, rank, world) for d, y in big]
+        local = [([None if t is None else t.contiguous() for t in d], y.contiguous()) for d, y in local]
+        finals = []
+        for captured in (False, True):
+            model, hp = build(mt, z, dims, mode=mode)
+            S.shard_model(model, tr)
+            model.train()
+            crit = R.MSELoss(hp)
+            opt = FusedAdam(model.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"], capturable=captured)
+            se = torch.zeros(1, device="cuda")
+            if captured:
+                steps = [CapturedStep(model, crit, opt, d, y, se, dist.group.WORLD, float(world), next_data=local[(i + 1) % len(local)][0])
+                         for i, (d, y) in enumerate(local)]
+                steps[0].prime()
+                for _ in range(2):
+                    for st in steps:
+                        st.replay()
+            else:
+                for _ in range(2):
+                    for d, y in local:
+                        model.zero_grad()
+                        out = model(d)
+                        e = crit(out, y, return_mean=False)
+                        se += e.detach().sum()
+                        torch.mean(e).backward()
+                        S.allreduce_dense_grads(model)
+                        opt.step()
+            torch.cuda.synchronize()
+            dist.all_reduce(se)
+            finals.append((S.gather_state_dict(model), float(se)))
+        if rank == 0:
+            (a, sa), (b, sb) = finals
+            assert abs(sa - sb) <= 1e-5 * abs(sa), (mt, sa, sb)
+            for k in a:
+                atol = hp["lr"] * 6 if (mt == "NARRE" and k.startswith("attention_scorer_") and k.endswith(".3.bias")) else 4e-6
+                assert_close(b[k], a[k], rtol=1e-4, atol=atol, msg="%s captured+prefetch vs eager: %s" % (mt, k))
+            print("dist_parity[%s, %s, world %d]: captured steps with prefetched lookups == eager sharded loop (SE sum %.6f)" % (mt, mode, world, sb), flush=True)
+        dist.barrier()
 
 
 if __name__ == "__main__":

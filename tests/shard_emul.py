@@ -11,14 +11,12 @@ class CpuKernels:
         flags[idx.reshape(-1)] = 1
 
     @staticmethod
-    def plan(flags, V, P, cap, req, slot):
-        slot.fill_(-1)
+    def plan(flags, V, P, cap, req):
         for o in range(P):
             local = torch.nonzero(flags[o::P]).reshape(-1)
             n = local.numel()
             req[o, 0] = n
-            req[o, 1:1 + n] = local
-            slot[local * P + o] = o * cap + torch.arange(n)
+            req[o, 1:1 + n] = local                   # the device appends in arbitrary order; any order is valid
         flags.zero_()
 
     @staticmethod
@@ -42,10 +40,14 @@ class CpuKernels:
             o[q, :n] = flat[rreq[q, 1:1 + n]]
 
     @staticmethod
-    def remap(idx, slot, out):
-        r = slot[idx]
-        assert int(r.min()) >= 0
-        out.copy_(r)
+    def place(rows, req, P, cap, cache, V):
+        r = rows.reshape(P, cap, -1)
+        c = cache.reshape(cache.shape[0], -1)
+        for q in range(P):
+            n = int(req[q, 0])
+            ids = req[q, 1:1 + n] * P + q
+            assert n == 0 or (int(ids.min()) >= 0 and int(ids.max()) < V)
+            c[ids] = r[q, :n]
 
     @staticmethod
     def gather(table, pos, out):

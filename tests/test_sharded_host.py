@@ -90,10 +90,11 @@ def _worker(rank, world, port, out):
         ids[:5] = R - 1                                       # a hot (pad-like) row
         w = torch.randn(n, L, generator=gr)
 
-        # ---- word table: one exchange, rows bit-exact through the remapped ids
+        # ---- word table: one exchange, rows bit-exact, read through the ORIGINAL token ids (id-indexed row cache)
         wt = sharded.ShardedWordTable(full_words, tr)
         da, db = wt.many(idx_a, idx_b)
-        assert da.table is db.table and da.table.shape == (world * wt.cap, E) and da.shadow is None
+        assert da.table is db.table and da.table.shape == (V, E) and da.shadow is None
+        assert da.idx is idx_a or torch.equal(da.idx, idx_a)
         assert torch.equal(da.table[da.idx], full_words[idx_a]) and torch.equal(db.table[db.idx], full_words[idx_b])
         assert int(wt._scratch(torch.device("cpu"))[0].sum()) == 0     # flags left clean for the next step
 
