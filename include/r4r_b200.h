@@ -131,6 +131,21 @@ int r4r_conv_set_clusters(int n);
  * writes the per-role cycle counters of its first CTA pair there (see conv_tc.cu); NULL turns it off. */
 int r4r_conv_debug_profile(void* buf32_u64);
 
+/* ---- K3: the whole DeepCoNN / DeepCoNN++ head in one forward and one backward kernel ---------------------------
+ * forward : fc_t(pooled_t) (common_pytorch_models.py:33-37) -> dropout (Philox in-kernel, or keep masks handed in) -> cat
+ *           (DeepCoNN.py:61) -> head 0: global_bias + TorchFM(cat) (DeepCoNN.py:64-66)  |  head 1: final MLP + user_bias[u] +
+ *           item_bias[i] + global_bias (DeepCoNN.py:69-72) -> rating [, (rating - y)^2 and its sum: loss.py:7-11]
+ * `ptrs` (25 device pointers, NULL where unused): pooled_u, pooled_i [N,F]; fc_u.w, fc_i.w [L,F]; fc_u.b, fc_i.b [L];
+ *   fm.V [2L,K], fm.lin.w [2L], fm.lin.b [1]; final.0.w [L,2L], final.0.b [L], final.3.w [L], final.3.b [1]; gathered
+ *   user_bias / item_bias values [N]; global_bias [1]; y [N]; keep masks uint8 [N,3L] (tests) ; int32 step counter;
+ *   OUT rating [N], se [N], se_sum [1] (+=), cat [N,2L], hid [N,L], keep uint32 [N,3].
+ * backward: `gptrs` (18): g_rating [N], g_se [N] (either may be NULL); OUT dpooled_u, dpooled_i [N,F]; ACCUMULATED d fc_u.w,
+ *   d fc_i.w, d fc_u.b, d fc_i.b, d fm.V, d fm.lin.w, d fm.lin.b, d final.0.w, d final.0.b, d final.3.w, d final.3.b; OUT
+ *   d user_bias values, d item_bias values [N]; ACCUMULATED d global_bias.  Also advances the step counter by one. */
+int r4r_deepconn_head_fwd(const void* const* ptrs, int N, int F, int L, int K, int head, float p, uint64_t seed, void* stream);
+int r4r_deepconn_head_bwd(const void* const* ptrs, const void* const* gptrs, int N, int F, int L, int K, int head, float p,
+                          void* stream);
+
 /* ---- a11: conv weight gradient through relu+max-pool (SURVEY.md finding 4) --------------------
  * dW[f,0,j,:] += sum_n gy[n,f] * Xpad[n, argmax[n,f]+j, :],  db[f] += sum_n gy[n,f]
  * with gy = gpooled * (pooled > 0).  Replaces autograd's convolution_backward + relu/max-pool

@@ -47,6 +47,8 @@ SIGNATURES = {
     "r4r_linear_bwd": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     "r4r_fm_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp]),
     "r4r_fm_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "r4r_deepconn_head_fwd": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_f32, ctypes.c_uint64, c_vp]),
+    "r4r_deepconn_head_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp]),
     "r4r_mse_fwd": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "r4r_mse_bwd": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "r4r_rows_argmax": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),

@@ -6,24 +6,33 @@
 // GEMM view per document: Y[p, f] = sum_{j<3} X[p+j-2, :] . W[f, j, :]   (M = T+2 positions,
 // N = filters, K = 3*E).  The three window rows are the SAME gathered rows shifted by one position,
 // so the A operand is staged ONCE per 128-position tile and the j-th GEMM reads it through a
-// shared-memory descriptor whose start address is advanced by j rows.  That only works if a row
-// shift is a constant byte offset, which is why the tile uses the no-swizzle "interleaved" K-major
-// UMMA layout stored chunk-major:
+// shared-memory descriptor whose start address is advanced by j rows.
 //
-//      A slot:  [chunk c = 8 consecutive embedding columns (16 B)] [row r] [16 B]
-//               address(r, c) = c * (RA*16) + r * 16
-//      -> 8x16B core matrices are contiguous (SBO = 128 B between 8-row groups),
-//         LBO = RA*16 B between the two K-chunks of one K=16 MMA, and row shift j = +16*j bytes.
+// TMA staging.  The rows are gathered by the tensor memory accelerator: one
+// cp.async.bulk.tensor.2d ... tile::gather4 instruction fetches 64 columns (128 B) of FOUR arbitrary rows
+// of the shadow table and writes them as four consecutive 128-byte rows of the canonical K-major
+// SWIZZLE_128B layout.  A ring slab = one 64-column block of a tile's 132 rows (128 + 2 halo + 2 spare);
+// row r lives at slab + r*128 with its 16-byte chunks XOR-ed by (r & 7).  The swizzle is a function of the
+// ABSOLUTE shared-memory address (slabs are 1024-byte aligned), so window row j is simply the descriptor
+// start address + j*128 with base_offset 0 (scripts/experiments/gather4_shift_test.cu: 2048/2048 outputs
+// exact for j = 0, 1, 2; base_offset = j is wrong), and a K=16 step is +32 B inside the 128-byte row.
+// Measured (scripts/experiments/gather4_bw.cu, profiles/r2_v3_gather4_staging_microbench.log; Zipf(1.0) tokens, 148
+// CTAs staging only): one issuing thread 0.81 ms per 1.65 M rows, 4 warps x 8 issuing lanes 0.150 ms = 7.1 TB/s; a warp's
+// copies issue lane after lane (~58 cycles each) and one SM's TMA unit retires a gather4 per ~20 cycles = 25 B/clk -- the
+// hot head of the Zipf distribution costs nothing (uniform ids: the same 0.150 ms).  Inside this kernel that rate is
+// BELOW the ~31 B/clk the tensor cores consume, so the TMA stages only the first slabs of every tile and a cp.async team
+// writes the rest into the same swizzled layout (see the warp roles); TMA alone: 0.451 ms per 4096 documents with seven
+// issuing warps, cp.async alone: 0.413 ms, the two together: 0.371 ms.
 //
 // CTA pair.  The filter bank W (B operand, 3*E x 100 fp16 = 180 KB) must stay resident in shared
 // memory next to the A ring, which one SM cannot hold, and a single-SM MMA of N <= 64 filters is
 // bound by shared-memory operand bandwidth (measured 57 instead of 32 cycles per MMA).  The kernel
 // therefore runs as clusters of two CTAs on one TPC issuing tcgen05.mma.cta_group::2 with
 // M = 256 positions x N = all filters: each CTA stages its own 128 positions of A and keeps HALF of
-// the filter bank; the pair's tensor cores read both halves.  Every document row is gathered
-// exactly once.
+// the filter bank (no-swizzle interleaved layout); the pair's tensor cores read both halves.  Every
+// document row is gathered exactly once.
 //
-// Warp roles per CTA (416 threads, 1 CTA/SM, persistent over documents):
+// Warp roles per CTA (512 threads x 128 registers, 1 CTA/SM, persistent over documents):
 //   warps 0-7   epilogue : tcgen05.ld of this CTA's 128 x N accumulator (warp w: TMEM lane quarter
 //                          w&3, column half w>>2) -> running max / tile-of-max in registers across
 //                          the tiles of a document -> per document two redux.sync per column (max,
@@ -31,35 +40,37 @@
 //                          a four-warp shared-memory merge -> the two CTAs' partial (max, argmax)
 //                          are merged through distributed shared memory (rank 1 stores into rank 0
 //                          with st.async) -> bias, ReLU, store
-//   warps 8-11  producer : cp.async.ca 16-byte gathers of the shadow-table rows into a ring of
-//                          K=64 slabs (8 chunk columns: each lane owns one column and nine rows, so a
-//                          copy's address is a per-row base + a compile-time offset); conv padding
-//                          rows read the all-zero row V of the shadow table; token ids are fetched
-//                          one tile ahead and document descriptors one document ahead; one mbarrier
-//                          arrival per warp per slab on the LEADER's barrier, `lag` slabs after issue
-//   warp  12    MMA      : allocates all 512 TMEM columns (both CTAs) = four accumulator buffers; in
+//   warps 8-11  cp.async : slabs tma_slabs.. of every tile: 16-byte gathers, each lane one chunk column of nine rows,
+//                          written at the swizzled address; asynchronous hand-off (cp.async.mbarrier.arrive.noinc:
+//                          no wait_group, no MEMBAR in the producer)
+//   warps 12-14 TMA      : slabs 0..tma_slabs-1 of every tile (2 of 5 at E = 300): eleven lanes per warp issue the
+//                          gather4 copies (a lane's four table rows stay in registers for the tile's slabs); both CTAs'
+//                          copies complete on the LEADER's barrier (.cta_group::2); conv padding rows fetch the all-zero
+//                          row V of the shadow table.  Both teams fetch token ids one tile ahead and document
+//                          descriptors one document ahead.
+//   warp  15    MMA      : allocates all 512 TMEM columns (both CTAs) = four accumulator buffers; in
 //                          the leader CTA one elected lane issues tcgen05.mma, multicast
 //                          tcgen05.commit releases ring slots ("empty") and publishes accumulators
-//                          ("tmem_full") in both CTAs
+//                          ("tmem_full") in both CTAs; in rank 1 one lane relays "my cp.async slab has landed" to
+//                          the leader, so the MMA warp waits on exactly one barrier per slab
 //
 // Work plan (docplan.cu): documents end in a run of one repeated padding token; every conv window
 // inside the run repeats a value max-pooling has already seen, so document n is processed as if it had
 // doc_len[n] = min(T, run start + 3) rows and arg-max positions >= doc_len are mapped back by
 // + (T - doc_len) -- bit-identical results, ~2.5x less work on Amazon-shaped batches -- and documents
 // are issued longest first.  Ragged input (tokens + offsets instead of padded ids) takes the same path.
-//
-// L1-allocating gathers matter: ~2/3 of all positions of Amazon-shaped documents are the pad token
-// and the rest is Zipfian, so with L2-only (cp.async.cg) loads all SMs queue on a handful of L2
-// lines (measured 33.7 ms vs 3.7 ms per 4096 documents).
 #include "common.cuh"
+#include <cuda.h>
 #include <stdlib.h>
 #include <type_traits>
 
 namespace {
 
 constexpr int TILE_M = 128;            // positions per CTA per accumulator tile (UMMA M = 256 per pair)
-constexpr int RA = 131;                // rows per A slot: 130 needed (128 + 2 halo); odd => the
-                                       // chunk stride RA*16 B maps 8 lanes onto 8 distinct bank groups
+constexpr int RS = 132;                // rows per A slab: 130 needed (128 + 2 halo) = 33 gather4 groups of 4
+constexpr int SLAB_BYTES = 17 * 1024;  // RS * 128 B rounded up to the 1024-byte swizzle period
+constexpr int NGROUPS = RS / 4;        // gather4 copies (row groups) per slab
+static_assert(RS * 128 <= SLAB_BYTES && RS % 4 == 0 && RS >= 130, "slab holds the tile's 128 rows + 2 halo rows in whole gather4 groups");
 constexpr int N_MAX = 128;             // filters (UMMA N), multiple of 16
 constexpr int ACC_STRIDE = 128;        // TMEM columns between consecutive accumulator buffers
 #ifndef R4R_NACC
@@ -68,18 +79,34 @@ constexpr int ACC_STRIDE = 128;        // TMEM columns between consecutive accum
 constexpr int NACC = R4R_NACC;         // accumulator buffers: the MMA warp may run three tiles ahead of the epilogue,
                                        // which hides the per-document reduction (the epilogue drains nothing meanwhile)
 constexpr int TMEM_COLS = NACC * ACC_STRIDE;   // 512 = all of TMEM (1 CTA per SM)
-constexpr int NUM_EPI_WARPS = 8, NUM_PROD_WARPS = 4;
+// Two producer teams share the slabs of a tile (8 epilogue + 4 + 3 producer + 1 MMA warp = 512 threads x 128 registers):
+//   TMA team   (3 warps): the first `tma_slabs` slabs of every tile (2 of 5 at E = 300).  A warp's TMA copies issue lane
+//                         after lane (~58 cycles each) and one SM's TMA unit retires a gather4 per ~20 cycles = 25 B/clk,
+//                         below the 31 B/clk the tensor cores consume -- TMA alone leaves the kernel copy-bound
+//                         (measured: 0.451 ms per 4096 documents with seven issuing warps, 0.529 ms with four).
+//   cp.async team (4 warps): the remaining slabs, written into the SAME swizzled layout (chunk c of row r at
+//                         r*128 + ((c ^ (r & 7)) << 4)); alone it is LSU-issue-bound (0.343 ms).
+// Together each team runs at about half of its ceiling and the kernel becomes tensor-pipe-bound.
+#ifndef R4R_LDG_WARPS
+#define R4R_LDG_WARPS 4
+#endif
+constexpr int NUM_EPI_WARPS = 8, NUM_LDG_WARPS = R4R_LDG_WARPS, NUM_TMA_WARPS = 7 - NUM_LDG_WARPS, NUM_PROD_WARPS = 7;
+constexpr int LDG_ROW_STEP = NUM_LDG_WARPS * 4;                                     // rows covered by one pass of the cp.async team
+constexpr int ROWS_PER_THREAD = (130 + LDG_ROW_STEP - 1) / LDG_ROW_STEP;          // cp.async thread i copies rows i/8 + LDG_ROW_STEP*k of ONE 16-byte chunk column
+static_assert(LDG_ROW_STEP % 8 == 0, "a thread's rows must share r & 7 (constant swizzled chunk)");
+constexpr int TMA_GROUPS_PER_LANE = (RS / 4 + NUM_TMA_WARPS * 32 - 1) / (NUM_TMA_WARPS * 32);   // 1 unless a single warp stages all 33 groups
 constexpr int MMA_WARP = NUM_EPI_WARPS + NUM_PROD_WARPS;
 constexpr int NUM_THREADS = (MMA_WARP + 1) * 32;
 constexpr int MAX_SLOTS = 8;
-constexpr int ROWS_PER_THREAD = 9;     // producer thread i copies rows i/8 + 16k, k < 9
-constexpr int CPS = 8;                 // 16-byte K-chunks per ring slab: one chunk column per producer lane (K = 64 per slab)
+constexpr int CPS = 8;                 // 16-byte K-chunks per ring slab (K = 64 = one 128-byte swizzled row per slab)
 constexpr int MAX_SPT = 16;            // slabs per position tile -> Kc <= 128 chunks (E <= 1024)
-constexpr int LAG = 2;                 // default: a slab is published after the next LAG ones have been issued
-constexpr int MAX_LAG = 4;             // tuning range (R4R_CONV_LAG); the ring needs lag + 2 slots
 
 struct SharedCtl {
-  unsigned long long full[MAX_SLOTS];      // leader's copy is used: 2 CTAs x NUM_PROD_WARPS arrivals
+  // "this CTA's slab has landed", one barrier per ring slot and producer team (a slot is used by either team, depending on
+  // the slab).  In the LEADER the same barriers also take one arrival from rank 1 (relayed by its idle MMA warp once ITS
+  // slab has landed), so the MMA warp waits on exactly one barrier per slab.
+  unsigned long long landed_t[MAX_SLOTS];  // TMA teams of BOTH CTAs -> the leader's copy: 2 x NUM_TMA_WARPS arrive.expect_tx + the bytes of both halves
+  unsigned long long landed_l[MAX_SLOTS];  // cp.async team: one asynchronous arrival per thread (cp.async.mbarrier.arrive.noinc) (+ 1 relay in the leader)
   unsigned long long empty[MAX_SLOTS];     // 1 arrival (multicast tcgen05.commit)
   unsigned long long tmem_full[NACC];      // 1 arrival (multicast tcgen05.commit)
   unsigned long long tmem_empty[NACC];     // leader's copy: 2 CTAs x NUM_EPI_WARPS arrivals
@@ -126,18 +153,26 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 __device__ __forceinline__ void mbar_arrive_cluster_n(uint32_t cluster_addr, uint32_t count) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0], %1;" :: "r"(cluster_addr), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" :: "r"(cluster_addr), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Every wait is bounded: a protocol bug must surface as a trapped launch (an error at the caller's next
+// synchronisation), never as a kernel that spins forever.  try_wait suspends the thread for a hardware-defined
+// interval per poll, so 2^26 failed polls are many seconds -- orders of magnitude beyond any legitimate wait.
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done;
+  uint32_t polls = 0;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (!done && ++polls == (1u << 26)) __trap();
   } while (!done);
 }
 // 4-byte store into another CTA's shared memory that signals completion (4 tx bytes) on a barrier there
@@ -149,21 +184,25 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// .ca keeps the gathered lines in L1 (see the header comment)
-template <int I, int N, typename F>
-__device__ __forceinline__ void static_for(F&& f) {
-  if constexpr (I < N) {
-    f(std::integral_constant<int, I>{});
-    static_for<I + 1, N>(f);
-  }
+// 16-byte asynchronous copies of the cp.async team (.ca: duplicate requests for a hot row merge in L1)
+__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
 }
-// 16-byte copy from [src + OFS] (compile-time byte offset folded into the instruction)
-template <int OFS>
-__device__ __forceinline__ void cp_async16_ca_ofs(uint32_t dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1+%2], 16;" :: "r"(dst), "l"(src), "n"(OFS) : "memory");
+// Arrival on `bar` that the hardware performs when all cp.async copies this thread has issued so far have landed:
+// the producer never waits for its own copies (no wait_group, no MEMBAR) -- the hand-off is fully asynchronous.
+__device__ __forceinline__ void cp_async_arrive_noinc(unsigned long long* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// One TMA gather4 copy: columns [col0, col0 + 64) of table rows r0..r3 -> four consecutive 128-byte rows at `dst`
+// (SWIZZLE_128B, this CTA's shared memory), 512 transaction bytes on the barrier `bar` -- a shared::cluster address:
+// with .cta_group::2 the completion may signal the PEER's barrier, so both CTAs' copies complete on the leader's.
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int col0, int r0, int r1, int r2, int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      :: "r"(dst), "l"(tmap), "r"(bar), "r"(col0), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -171,9 +210,9 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 __device__ __forceinline__ uint64_t mk_desc(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
-// UMMA shared-memory descriptor (K-major, SWIZZLE_NONE = layout_type 0, version 1 for sm_100):
-// bits 0-13 start address >> 4, 16-29 LBO >> 4, 32-45 SBO >> 4, bit 46 version.  mma_role() keeps
-// the two 32-bit halves and advances the address field by constants.
+// UMMA shared-memory descriptor (K-major, version 1 for sm_100): bits 0-13 start address >> 4, 16-29 LBO >> 4,
+// 32-45 SBO >> 4, bit 46 version, 61-63 layout type (0 = no swizzle: the filter bank; 2 = SWIZZLE_128B: the
+// TMA-written A slabs).  mma_role() keeps the two 32-bit halves and advances the address field by constants.
 // instruction descriptor: D=f32, A/B = f16 (0) or bf16 (1), both K-major, M=256 (pair), N=n
 __device__ __forceinline__ uint32_t umma_idesc(int fmt, int n) {
   return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)((2 * TILE_M) >> 4) << 24);
@@ -230,8 +269,8 @@ struct Params {
   int fmt;                   // 0 f16, 1 bf16
   int nslots;
   int slot_bytes;
+  int tma_slabs;             // slabs 0 .. tma_slabs-1 of every tile are staged by TMA, the rest by cp.async
   unsigned long long* prof;  // diagnostics: per-role cycle counters of cluster 0 (r4r_conv_debug_profile), or NULL
-  int lag;                   // slabs issued ahead of the one being published (1..MAX_LAG)
   const int* doc_len;        // [N] effective document lengths (r4r_doc_plan), or NULL = T for every document
   const int* doc_order;      // [N] processing order (longest first), or NULL = identity
 };
@@ -427,120 +466,213 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
   }
 }
 
-template <int LAGT>
-__device__ __forceinline__ void producer_role(const Params& P, SharedCtl* ctl, uint8_t* ring, uint32_t rank, int cluster_id,
-                                              int nclusters, int ptid) {
-  const int spt = (P.Kc + CPS - 1) / CPS;                // slabs per tile
-  const int c8 = ptid & 7, r0 = ptid >> 3;
-  const int lane = ptid & 31;
-  const uint32_t ring_base = smem_u32(ring);
-  const uint32_t dst_thread = (uint32_t)(c8 * RA * 16 + r0 * 16);
-  const int nslots = P.nslots;
-  const uint32_t leader_full0 = mapa(smem_u32(&ctl->full[0]), 0);
-  const bool last_row = r0 + 16 * (ROWS_PER_THREAD - 1) < TILE_M + 2;   // rows 128, 129 exist for r0 < 2 only
-  // every producer lane copies ONE 16-byte chunk column (c8 + 8s in slab s) of its nine rows, so the
-  // global address of a copy is a per-row base + a compile-time offset (no address arithmetic per copy);
-  // conv padding rows read the all-zero row V of the shadow table (no src-size operand either)
-  const uint8_t* const thread_base = P.shadow + c8 * 16;
-  const uint8_t* const zero_row = thread_base + P.V * P.row_bytes;
-  const int last_slab_chunks = P.Kc - (spt - 1) * CPS;                  // chunk columns in the last slab
-  const bool in_last = c8 < last_slab_chunks;
-
-  // Token ids of a tile's rows are fetched ONE TILE AHEAD into registers (unchecked, so the nine
-  // loads are issued back to back and their HBM latency hides behind the current tile's slabs);
-  // slot row r <-> document position pt*256 + rank*128 - 2 + r, -1 marks a zero (padding) row.
-  auto fetch = [&](const DocRef& d, int pt, long long (&out)[ROWS_PER_THREAD]) {
-    if (P.tok32 == nullptr) {
-      const long long* drow = P.idx + d.doc * (long long)P.T;
-#pragma unroll
-      for (int k = 0; k < ROWS_PER_THREAD; ++k) {
-        const int r = r0 + 16 * k;
-        const int pos = pt * 2 * TILE_M + (int)rank * TILE_M - 2 + r;
-        out[k] = (r < TILE_M + 2 && pos >= 0 && pos < d.Td) ? __ldg(drow + pos) : -1LL;
-      }
+// Work items of the producers: (document, tile) pairs of this CTA pair in launch order, with the document descriptors
+// fetched a whole document ahead (their loads never stall the token-id prefetch of the document's first tile).
+struct TileWalk {
+  long long wk;
+  int pt;
+  DocRef cur_d, nxt_d;
+  __device__ __forceinline__ void init(const Params& P, int cluster_id, int nclusters) {
+    wk = cluster_id;
+    pt = 0;
+    cur_d.doc = nxt_d.doc = 0; cur_d.Td = nxt_d.Td = 0; cur_d.npt = nxt_d.npt = 1; cur_d.base = nxt_d.base = 0; cur_d.len = nxt_d.len = 0;
+    if (wk < P.N) {
+      cur_d = doc_ref(P, wk);
+      if (wk + nclusters < P.N) nxt_d = doc_ref(P, wk + nclusters);
+    }
+  }
+  // the tile after the current one: (has_next, its document, its tile index)
+  __device__ __forceinline__ bool peek(const Params& P, int nclusters, const DocRef*& d, int& pt_next) const {
+    const bool wrap = pt + 1 == cur_d.npt;
+    d = wrap ? &nxt_d : &cur_d;
+    pt_next = wrap ? 0 : pt + 1;
+    return (wrap ? wk + nclusters : wk) < P.N;
+  }
+  __device__ __forceinline__ void advance(const Params& P, int nclusters) {
+    const bool wrap = pt + 1 == cur_d.npt;
+    if (wrap) {
+      wk += nclusters;
+      cur_d = nxt_d;
+      if (wk + nclusters < P.N) nxt_d = doc_ref(P, wk + nclusters);
+      pt = 0;
     } else {
-      const int* drow = P.tok32 + d.base;
+      ++pt;
+    }
+  }
+};
+
+// token id of slab row r of tile pt of document d (slab row r <-> document position pt*256 + rank*128 - 2 + r);
+// -1 = a zero (conv padding) row.  Unchecked: callers validate when the value is consumed, a tile later.
+__device__ __forceinline__ long long slab_token(const Params& P, const DocRef& d, int pt, uint32_t rank, int r) {
+  const int pos = pt * 2 * TILE_M + (int)rank * TILE_M - 2 + r;
+  if (!(r < TILE_M + 2 && pos >= 0 && pos < d.Td)) return -1;
+  if (P.tok32 == nullptr) return __ldg(P.idx + d.doc * (long long)P.T + pos);
+  return pos < d.len ? (long long)__ldg(P.tok32 + d.base + pos) : P.pad_id;
+}
+
+// ---- TMA team: slabs 0 .. tma_slabs-1 of every tile.  Row group g (rows 4g .. 4g+3) of a slab belongs to lane
+// g / NUM_TMA_WARPS of TMA warp g % NUM_TMA_WARPS; the four table rows stay in registers for the tile's slabs.
+__device__ __forceinline__ void tma_role(const Params& P, const CUtensorMap* tmap, SharedCtl* ctl, uint8_t* ring, uint32_t rank,
+                                         int cluster_id, int nclusters, int pwarp, int lane) {
+  // row group g of a slab (rows 4g .. 4g+3): warp g % NUM_TMA_WARPS, lane (g / NUM_TMA_WARPS) % 32, the lane's j-th group
+  constexpr int GPL = TMA_GROUPS_PER_LANE;
+  const int warp_groups = (NGROUPS - pwarp + NUM_TMA_WARPS - 1) / NUM_TMA_WARPS;     // groups of this warp
+  int grp[GPL], my_groups = 0;
 #pragma unroll
-      for (int k = 0; k < ROWS_PER_THREAD; ++k) {
-        const int r = r0 + 16 * k;
-        const int pos = pt * 2 * TILE_M + (int)rank * TILE_M - 2 + r;
-        const bool in_doc = r < TILE_M + 2 && pos >= 0 && pos < d.Td;
-        const int t = (in_doc && pos < d.len) ? __ldg(drow + pos) : (int)P.pad_id;
-        out[k] = in_doc ? (long long)t : -1LL;
-      }
+  for (int j = 0; j < GPL; ++j) {
+    grp[j] = (lane + 32 * j) * NUM_TMA_WARPS + pwarp;
+    if (lane + 32 * j < warp_groups) ++my_groups;
+  }
+  if (my_groups == 0) return;                            // TMA copies are per-thread instructions: the other lanes have nothing to do
+  const int spt = (P.Kc + CPS - 1) / CPS;                // slabs per tile
+  const uint32_t ring_base = smem_u32(ring);
+  const uint32_t nslots = (uint32_t)P.nslots;
+  const uint32_t warp_bytes = (uint32_t)warp_groups * 512u;                           // this warp's share of a slab
+  const uint32_t leader_t0 = mapa(smem_u32(&ctl->landed_t[0]), 0);                    // both CTAs' TMA copies complete on the leader's barriers
+  const int zero_row = (int)P.V;                         // row V of the shadow table is all zero (conv padding)
+  const unsigned issue_mask = __activemask();
+  auto rows_of = [&](const long long (&tok)[4], int (&out)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (tok[k] < -1 || tok[k] >= P.V) __trap();        // the reference device-asserts on OOB ids
+      out[k] = tok[k] < 0 ? zero_row : (int)tok[k];
     }
   };
-  // publish a slab: its copies have landed (wait_group), make them visible to the tensor cores
-  // (async proxy), then ONE arrival per warp on the leader CTA's barrier
-  uint32_t sig_slot = 0;
-  auto publish = [&]() {
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) mbar_arrive_cluster(leader_full0 + sig_slot * 8u);
-    sig_slot = sig_slot + 1 == (uint32_t)nslots ? 0u : sig_slot + 1;
-  };
-
   const bool prof_on = P.prof != nullptr && cluster_id == 0;
-  long long w_empty = 0, w_group = 0, t_begin = clock64();
-  uint32_t slot = 0, empty_parity = 1u;                  // parity the empty barrier shows once the slot is free
-  uint32_t pending = 0;                                  // slabs issued but not yet published
-  // `cur` = the work item being copied, `nxt` = the one after it: its order / length / offsets are loaded
-  // a whole document ahead so that the token-id prefetch of its first tile never waits on them
-  long long wk = cluster_id;
-  int pt = 0;
-  DocRef cur_d, nxt_d;
-  cur_d.doc = nxt_d.doc = 0; cur_d.Td = nxt_d.Td = 0; cur_d.npt = nxt_d.npt = 1; cur_d.base = nxt_d.base = 0; cur_d.len = nxt_d.len = 0;
-  long long cur[ROWS_PER_THREAD], nxt[ROWS_PER_THREAD];
-  if (wk < P.N) {
-    cur_d = doc_ref(P, wk);
-    if (wk + nclusters < P.N) nxt_d = doc_ref(P, wk + nclusters);
-    fetch(cur_d, 0, cur);
+  long long w_empty = 0, w_issue = 0, t_begin = clock64();
+  TileWalk W;
+  W.init(P, cluster_id, nclusters);
+  int cur[GPL][4];
+  long long nxt[GPL][4];
+#pragma unroll
+  for (int j = 0; j < GPL; ++j) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) nxt[j][k] = (W.wk < P.N && j < my_groups) ? slab_token(P, W.cur_d, 0, rank, 4 * grp[j] + k) : -1;
+    rows_of(nxt[j], cur[j]);
   }
-  while (wk < P.N) {
-    const bool wrap = pt + 1 == cur_d.npt;
-    const long long nk = wrap ? wk + nclusters : wk;
-    const int pt_next = wrap ? 0 : pt + 1;
-    if (nk < P.N) fetch(wrap ? nxt_d : cur_d, pt_next, nxt);
+  uint32_t slab = 0;                                     // running slab index of this CTA: slot = slab % nslots, use = slab / nslots
+  while (W.wk < P.N) {
+    const DocRef* nd;
+    int pt_next;
+    const bool more = W.peek(P, nclusters, nd, pt_next);
+    if (more) {
+#pragma unroll
+      for (int j = 0; j < GPL; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) nxt[j][k] = j < my_groups ? slab_token(P, *nd, pt_next, rank, 4 * grp[j] + k) : -1;
+    }
+    for (int s = 0; s < P.tma_slabs; ++s) {
+      const uint32_t slot = (slab + s) % nslots, use = (slab + s) / nslots;
+      TIMED_WAIT(w_empty, mbar_wait(&ctl->empty[slot], (use & 1u) ^ 1u));
+      const uint32_t bar = leader_t0 + slot * 8u;
+      if (lane == 0) mbar_arrive_expect_tx_cluster(bar, warp_bytes);
+      __syncwarp(issue_mask);
+      const long long t_i = prof_on ? clock64() : 0;
+#pragma unroll
+      for (int j = 0; j < GPL; ++j)
+        if (j < my_groups)
+          tma_gather4(ring_base + slot * (uint32_t)SLAB_BYTES + (uint32_t)grp[j] * 512u, tmap, bar, s * CPS * 8, cur[j][0], cur[j][1], cur[j][2], cur[j][3]);
+      if (prof_on) w_issue += clock64() - t_i;
+    }
+    slab += (uint32_t)spt;
+    if (more) {
+#pragma unroll
+      for (int j = 0; j < GPL; ++j) rows_of(nxt[j], cur[j]);
+    }
+    W.advance(P, nclusters);
+  }
+  if (prof_on && pwarp == 0 && lane == 0) {
+    unsigned long long* o = P.prof + rank * 16 + 4;
+    o[0] = (unsigned long long)(clock64() - t_begin); o[1] = w_empty; o[2] = w_issue;
+  }
+}
+
+// ---- cp.async team: slabs tma_slabs .. spt-1 of every tile, in the same 128-byte-swizzled layout.  Every lane copies ONE
+// 16-byte chunk column c8 of its nine rows r0 + 16k (r & 7 is the same for all of them, so the swizzled chunk is a
+// per-thread constant).  The hand-off is asynchronous: after issuing its copies of a slab every thread posts a
+// cp.async.mbarrier.arrive.noinc, which the hardware turns into an arrival once those copies have landed -- no
+// wait_group, no MEMBAR in the producer (round 1's producer stalled ~700 cycles per slab on exactly that); the
+// consumer side (MMA warp / relay) executes the generic->async proxy fence after the barrier completes.
+__device__ __forceinline__ void ldg_role(const Params& P, SharedCtl* ctl, uint8_t* ring, uint32_t rank, int cluster_id, int nclusters,
+                                         int ptid) {
+  const int spt = (P.Kc + CPS - 1) / CPS;
+  if (P.tma_slabs >= spt) return;                        // narrow rows: the TMA team stages everything
+  const int c8 = ptid & 7, r0 = ptid >> 3;
+  const uint32_t ring_base = smem_u32(ring);
+  const uint32_t dst_thread = (uint32_t)(r0 * 128 + ((c8 ^ (r0 & 7)) << 4));
+  const uint32_t nslots = (uint32_t)P.nslots;
+  const bool last_row = r0 + LDG_ROW_STEP * (ROWS_PER_THREAD - 1) < TILE_M + 2;   // the last pass only reaches rows < 130
+  const uint8_t* const thread_base = P.shadow + c8 * 16;
+  const uint8_t* const zero_row = thread_base + P.V * P.row_bytes;
+  const int last_slab_chunks = P.Kc - (spt - 1) * CPS;                  // chunk columns the MMA reads in the last slab
+  const bool in_last = c8 < last_slab_chunks;
+  const bool prof_on = P.prof != nullptr && cluster_id == 0;
+  long long w_empty = 0, t_begin = clock64();
+  TileWalk W;
+  W.init(P, cluster_id, nclusters);
+  long long cur[ROWS_PER_THREAD], nxt[ROWS_PER_THREAD];
+#pragma unroll
+  for (int k = 0; k < ROWS_PER_THREAD; ++k) cur[k] = W.wk < P.N ? slab_token(P, W.cur_d, 0, rank, r0 + LDG_ROW_STEP * k) : -1;
+  uint32_t slab = 0;
+  while (W.wk < P.N) {
+    const DocRef* nd;
+    int pt_next;
+    const bool more = W.peek(P, nclusters, nd, pt_next);
+    if (more) {
+#pragma unroll
+      for (int k = 0; k < ROWS_PER_THREAD; ++k) nxt[k] = slab_token(P, *nd, pt_next, rank, r0 + LDG_ROW_STEP * k);
+    }
     const uint8_t* src[ROWS_PER_THREAD];
 #pragma unroll
     for (int k = 0; k < ROWS_PER_THREAD; ++k) {
-      const long long tok = cur[k];
-      if (tok < -1 || tok >= P.V) __trap();               // the reference device-asserts on OOB ids
-      src[k] = tok < 0 ? zero_row : thread_base + tok * P.row_bytes;
+      if (cur[k] < -1 || cur[k] >= P.V) __trap();        // the reference device-asserts on OOB ids
+      src[k] = cur[k] < 0 ? zero_row : thread_base + cur[k] * P.row_bytes;
     }
-    static_for<0, MAX_SPT>([&](auto sc) {
-      constexpr int s = decltype(sc)::value;
-      if (s < spt) {
-        TIMED_WAIT(w_empty, mbar_wait(&ctl->empty[slot], empty_parity));
-        const uint32_t dst = ring_base + slot * (uint32_t)P.slot_bytes + dst_thread;
-        if (s < spt - 1 || in_last) {
+    for (int s = P.tma_slabs; s < spt; ++s) {
+      const uint32_t slot = (slab + s) % nslots, use = (slab + s) / nslots;
+      TIMED_WAIT(w_empty, mbar_wait(&ctl->empty[slot], (use & 1u) ^ 1u));
+      const uint32_t dst = ring_base + slot * (uint32_t)SLAB_BYTES + dst_thread;
+      if (s < spt - 1 || in_last) {
+        const int cofs = s * CPS * 16;
 #pragma unroll
-          for (int k = 0; k < ROWS_PER_THREAD - 1; ++k) cp_async16_ca_ofs<s * CPS * 16>(dst + k * 256, src[k]);
-          if (last_row) cp_async16_ca_ofs<s * CPS * 16>(dst + (ROWS_PER_THREAD - 1) * 256, src[ROWS_PER_THREAD - 1]);
-        }
-        cp_async_commit();
-        ++pending;
-        if (pending > (uint32_t)LAGT) {
-          TIMED_WAIT(w_group, cp_async_wait<LAGT>(); publish());
-          --pending;
-        }
-        if (++slot == (uint32_t)nslots) { slot = 0; empty_parity ^= 1u; }
+        for (int k = 0; k < ROWS_PER_THREAD - 1; ++k) cp_async16_ca(dst + k * (LDG_ROW_STEP * 128), src[k] + cofs);
+        if (last_row) cp_async16_ca(dst + (ROWS_PER_THREAD - 1) * (LDG_ROW_STEP * 128), src[ROWS_PER_THREAD - 1] + cofs);
       }
-    });
-#pragma unroll
-    for (int k2 = 0; k2 < ROWS_PER_THREAD; ++k2) cur[k2] = nxt[k2];
-    if (wrap) {
-      cur_d = nxt_d;
-      if (nk + nclusters < P.N) nxt_d = doc_ref(P, nk + nclusters);   // consumed a document later
+      cp_async_arrive_noinc(&ctl->landed_l[slot]);
     }
-    wk = nk;
-    pt = pt_next;
+    slab += (uint32_t)spt;
+#pragma unroll
+    for (int k = 0; k < ROWS_PER_THREAD; ++k) cur[k] = nxt[k];
+    W.advance(P, nclusters);
   }
-  cp_async_wait<0>();
-  for (; pending > 0; --pending) publish();
   if (prof_on && ptid == 0) {
-    unsigned long long* o = P.prof + rank * 16 + 4;
-    o[0] = (unsigned long long)(clock64() - t_begin); o[1] = w_empty; o[2] = w_group;
+    unsigned long long* o = P.prof + rank * 16 + 12;
+    o[0] = (unsigned long long)(clock64() - t_begin); o[1] = w_empty; o[2] = 0;
+  }
+}
+
+// Rank 1's otherwise idle MMA warp: tells the leader when each cp.async slab of THIS CTA has landed (the asynchronous
+// arrivals of cp.async can only target a barrier of their own CTA; the pair's MMA is issued by rank 0).  TMA slabs need
+// no relay: their copies complete on the leader's barrier directly.
+__device__ __forceinline__ void relay_role(const Params& P, SharedCtl* ctl, int cluster_id, int nclusters) {
+  const int spt = (P.Kc + CPS - 1) / CPS;
+  const uint32_t leader_l0 = mapa(smem_u32(&ctl->landed_l[0]), 0);
+  const uint32_t nslots = (uint32_t)P.nslots;
+  uint32_t slab = 0, par_l = 0u;                         // per-slot phase parity of landed_l (bit = slot)
+  for (long long k = cluster_id; k < P.N; k += nclusters) {
+    long long doc;
+    int Td;
+    work_item(P, k, doc, Td);
+    const int npt = tiles_of(Td);
+    for (int pt = 0; pt < npt; ++pt)
+      for (int s = 0; s < spt; ++s, ++slab) {
+        const uint32_t slot = slab % nslots;
+        if (s >= P.tma_slabs) {
+          mbar_wait(&ctl->landed_l[slot], (par_l >> slot) & 1u); par_l ^= 1u << slot;
+          fence_proxy_async();                            // cp.async wrote through the generic proxy, the tensor cores read through the async proxy
+          mbar_arrive_cluster(leader_l0 + slot * 8u);
+        }
+      }
   }
 }
 
@@ -549,17 +681,20 @@ __device__ __forceinline__ void mma_role(const Params& P, SharedCtl* ctl, const 
   const int spt = (P.Kc + CPS - 1) / CPS;
   const uint32_t idesc = umma_idesc(P.fmt, P.Npad);
   const uint32_t a_base = smem_u32(ring), b_base = smem_u32(bsm);
-  const uint32_t a_lbo = RA * 16, b_lbo = (uint32_t)(P.Npad / 2) * 16;
+  const uint32_t b_lbo = (uint32_t)(P.Npad / 2) * 16;
   const int nslots = P.nslots;
-  // low descriptor word = start address >> 4 | LBO >> 4 << 16, high word = SBO (128 B) >> 4 | version 1
-  const uint32_t desc_hi = (128u >> 4) | (1u << 14);
-  const uint32_t a_step = a_lbo >> 4, b_step = b_lbo >> 4;      // one 16-byte K-chunk
-  const uint32_t a_j = 1u;                   // window row j: +16 bytes in the A slot
+  // low descriptor word = start address >> 4 | LBO >> 4 << 16; high word = SBO >> 4 | version 1 | layout type << 29
+  //   A (TMA-written, SWIZZLE_128B): SBO = 1024 B between 8-row groups, LBO unused (1), layout type 2
+  //   B (filter bank, no swizzle)  : SBO = 128 B, LBO = distance between the two K-chunks of a K=16 step
+  const uint32_t a_desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  const uint32_t b_desc_hi = (128u >> 4) | (1u << 14);
+  const uint32_t b_step = b_lbo >> 4;                           // one 16-byte K-chunk of the filter bank
+  const uint32_t a_j = 128u >> 4;                               // window row j: +128 bytes (one row) in the A slab
   const uint32_t b_j = (uint32_t)P.Kc * b_step;                 //               +Kc chunks in the filter bank
-  const uint32_t a_lo0 = ((a_base >> 4) & 0x3FFFu) | (a_step << 16);
+  const uint32_t a_lo0 = ((a_base >> 4) & 0x3FFFu) | (1u << 16);
   const uint32_t b_lo0 = ((b_base >> 4) & 0x3FFFu) | (b_step << 16);
   const bool leader = elect_one();
-  uint32_t slot = 0, full_parity = 0u, it = 0;
+  uint32_t slot = 0, it = 0, par_t = 0u, par_l = 0u;     // par_*: per-slot phase parity of the landed barriers (bit = slot)
   const bool prof_on = P.prof != nullptr && cluster_id == 0;
   long long w_tmem = 0, w_full = 0, t_begin = clock64();
   for (long long k = cluster_id; k < P.N; k += nclusters) {
@@ -573,27 +708,30 @@ __device__ __forceinline__ void mma_role(const Params& P, SharedCtl* ctl, const 
       tc_fence_after();
       const uint32_t d_tmem = ctl->tmem_base + buf * ACC_STRIDE;
       for (int s = 0; s < spt; ++s) {
-        TIMED_WAIT(w_full, mbar_wait(&ctl->full[slot], full_parity));              // both CTAs' producers published this slab
+        // both CTAs' halves of the slab have landed (this CTA's team + the relayed arrival of rank 1)
+        if (s < P.tma_slabs) { TIMED_WAIT(w_full, mbar_wait(&ctl->landed_t[slot], (par_t >> slot) & 1u)); par_t ^= 1u << slot; }
+        else                 { TIMED_WAIT(w_full, mbar_wait(&ctl->landed_l[slot], (par_l >> slot) & 1u)); par_l ^= 1u << slot; fence_proxy_async(); }
         tc_fence_after();
         if (leader) {
-          // descriptors advance by constants: +2 K-chunks per K=16 step, +1 row (16 B) per window row j
+          // descriptors advance by constants: a K=16 step is +32 B inside the swizzled 128-byte A row and +2 K-chunks in
+          // the filter bank; window row j is +128 B (one row) in the A slab
           const int nk = min(CPS, P.Kc - s * CPS) >> 1;        // K=16 steps in this slab
-          uint32_t a_lo = a_lo0 + ((slot * (uint32_t)P.slot_bytes) >> 4);
+          uint32_t a_lo = a_lo0 + ((slot * (uint32_t)SLAB_BYTES) >> 4);
           uint32_t b_lo = b_lo0 + (uint32_t)(s * CPS) * b_step;
           uint32_t acc = s ? 1u : 0u;
           for (int kk = 0; kk < nk; ++kk) {
-            umma_f16_pair(d_tmem, mk_desc(a_lo, desc_hi), mk_desc(b_lo, desc_hi), idesc, acc);
-            umma_f16_pair(d_tmem, mk_desc(a_lo + a_j, desc_hi), mk_desc(b_lo + b_j, desc_hi), idesc, 1u);
-            umma_f16_pair(d_tmem, mk_desc(a_lo + 2 * a_j, desc_hi), mk_desc(b_lo + 2 * b_j, desc_hi), idesc, 1u);
+            umma_f16_pair(d_tmem, mk_desc(a_lo, a_desc_hi), mk_desc(b_lo, b_desc_hi), idesc, acc);
+            umma_f16_pair(d_tmem, mk_desc(a_lo + a_j, a_desc_hi), mk_desc(b_lo + b_j, b_desc_hi), idesc, 1u);
+            umma_f16_pair(d_tmem, mk_desc(a_lo + 2 * a_j, a_desc_hi), mk_desc(b_lo + 2 * b_j, b_desc_hi), idesc, 1u);
             acc = 1u;
-            a_lo += 2 * a_step;
+            a_lo += 32u >> 4;
             b_lo += 2 * b_step;
           }
           umma_commit_pair(&ctl->empty[slot]);                      // slot reusable (both CTAs) once these MMAs retire
           if (s == spt - 1) umma_commit_pair(&ctl->tmem_full[buf]); // accumulator complete (both CTAs)
         }
         __syncwarp();
-        if (++slot == (uint32_t)nslots) { slot = 0; full_parity ^= 1u; }
+        if (++slot == (uint32_t)nslots) slot = 0;
       }
     }
   }
@@ -603,7 +741,8 @@ __device__ __forceinline__ void mma_role(const Params& P, SharedCtl* ctl, const 
   }
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv_pool_tc_kernel(const __grid_constant__ Params P) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv_pool_tc_kernel(const __grid_constant__ Params P,
+                                                                                                 const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -614,10 +753,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
   // identical carve-up in both CTAs: the pair's MMA addresses both through one descriptor
   SharedCtl* ctl = reinterpret_cast<SharedCtl*>(smem);
   uint8_t* bsm = smem + ((sizeof(SharedCtl) + 127u) & ~127u);
-  uint8_t* ring = bsm + ((b_bytes + 127u) & ~127u);
+  // the ring starts on a 1024-byte boundary of the shared-memory WINDOW (the 128-byte swizzle is a function of the
+  // absolute address; both CTAs get the same offset because their dynamic segments start at the same window offset)
+  uint8_t* ring = smem + (((smem_u32(bsm) + ((b_bytes + 127u) & ~127u) + 1023u) & ~1023u) - smem_u32(smem));
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < MAX_SLOTS; ++i) { mbar_init(&ctl->full[i], 2 * NUM_PROD_WARPS); mbar_init(&ctl->empty[i], 1); }
+    for (int i = 0; i < MAX_SLOTS; ++i) {
+      const uint32_t relay = rank == 0 ? 1u : 0u;
+      mbar_init(&ctl->landed_t[i], 2 * NUM_TMA_WARPS); mbar_init(&ctl->landed_l[i], NUM_LDG_WARPS * 32 + relay);
+      mbar_init(&ctl->empty[i], 1);
+    }
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap) : "memory");
     for (int i = 0; i < NACC; ++i) {
       mbar_init(&ctl->tmem_full[i], 1);
       mbar_init(&ctl->tmem_empty[i], 2 * NUM_EPI_WARPS);
@@ -655,16 +801,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
       case 56: epilogue_role<56>(P, ctl, rank, cluster_id, nclusters, warp, lane); break;
       default: epilogue_role<64>(P, ctl, rank, cluster_id, nclusters, warp, lane); break;
     }
+  } else if (warp < NUM_EPI_WARPS + NUM_LDG_WARPS) {
+    ldg_role(P, ctl, ring, rank, cluster_id, nclusters, threadIdx.x - NUM_EPI_WARPS * 32);
   } else if (warp < MMA_WARP) {
-    const int ptid = threadIdx.x - NUM_EPI_WARPS * 32;
-    switch (P.lag) {
-      case 1:  producer_role<1>(P, ctl, ring, rank, cluster_id, nclusters, ptid); break;
-      case 3:  producer_role<3>(P, ctl, ring, rank, cluster_id, nclusters, ptid); break;
-      case 4:  producer_role<4>(P, ctl, ring, rank, cluster_id, nclusters, ptid); break;
-      default: producer_role<2>(P, ctl, ring, rank, cluster_id, nclusters, ptid); break;
-    }
+    tma_role(P, &tmap, ctl, ring, rank, cluster_id, nclusters, warp - NUM_EPI_WARPS - NUM_LDG_WARPS, lane);
   } else if (rank == 0) {
     mma_role(P, ctl, bsm, ring, cluster_id, nclusters, lane);
+  } else if (lane == 0) {
+    relay_role(P, ctl, cluster_id, nclusters);
   }
 
   tc_fence_before();
@@ -765,6 +909,7 @@ static int conv_pool_tc_launch(const void* shadow, int64_t V, int Epad, int E, i
   PackPlan pl;
   R4R_REQUIRE(make_plan(E, F, pl), R4R_EUNSUP, "conv_pool_tc: E=%d F=%d unsupported (F <= %d)", E, F, N_MAX);
   R4R_REQUIRE(Epad % 8 == 0 && Epad >= pl.Kc * 8, R4R_EINVAL, "conv_pool_tc: shadow row width Epad=%d must be a multiple of 8 and >= %d", Epad, pl.Kc * 8);
+  R4R_REQUIRE(V + 1 < (1LL << 31), R4R_EUNSUP, "conv_pool_tc: V=%lld exceeds the TMA row coordinate range", (long long)V);
   // NOTE: the shadow table must carry V+1 rows, row V all zero (r4r_shadow_build writes it): conv padding rows are read from it
   R4R_REQUIRE(reinterpret_cast<uintptr_t>(shadow) % 16 == 0 && reinterpret_cast<uintptr_t>(wpack) % 16 == 0, R4R_EINVAL, "conv_pool_tc: shadow/wpack must be 16-byte aligned");
   if (N == 0) return 0;
@@ -780,23 +925,41 @@ static int conv_pool_tc_launch(const void* shadow, int64_t V, int Epad, int E, i
     R4R_REQUIRE(cc == 10, R4R_ENODEV, "conv_pool_tc: needs an sm_100 device (found cc %d.x)", cc);
     R4R_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
-  // shared-memory plan: [ctl][resident filter half][A ring of nslots x (CPS chunks x RA rows x 16 B)]
+  // shared-memory plan: [ctl][resident filter half][pad to 1024][A ring of nslots x SLAB_BYTES]
   const long long ctl_bytes = (sizeof(SharedCtl) + 127) & ~127LL;
   const long long b_bytes = (pl.half_bytes + 127) & ~127LL;
-  const long long avail = (long long)smem_optin - ctl_bytes - b_bytes - 1024;
+  const long long avail = (long long)smem_optin - ctl_bytes - b_bytes - 1024;      // 1024: worst-case alignment pad of the ring
   R4R_REQUIRE(pl.Kc <= CPS * MAX_SPT, R4R_EUNSUP, "conv_pool_tc: E=%d exceeds %d", E, CPS * MAX_SPT * 8);
-  long long ns = avail / ((long long)CPS * RA * 16);
+  long long ns = avail / SLAB_BYTES;
   if (ns > MAX_SLOTS) ns = MAX_SLOTS;
   const int nslots = (int)ns;
-  int lag = LAG;
-  {
-    const char* e = getenv("R4R_CONV_LAG");                 // tuning override
-    if (e && atoi(e) >= 1 && atoi(e) <= MAX_LAG) lag = atoi(e);
-    if (lag > nslots - 2) lag = nslots - 2;
+  R4R_REQUIRE(nslots >= 3, R4R_EUNSUP, "conv_pool_tc: E=%d F=%d leaves no room for the A ring next to the filter bank", E, F);
+  const size_t smem_bytes = (size_t)(ctl_bytes + b_bytes + 1024 + (long long)nslots * SLAB_BYTES);
+
+  // tensor map of the shadow table for the gather4 copies: [V+1 rows][Epad columns] half-precision, box = 64 columns x 1 row
+  // (four such rows per instruction), SWIZZLE_128B; columns past Epad (a last, partial block) are zero-filled by the TMA
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    cudaDriverEntryPointQueryResult qres;
+    void* fn = nullptr;
+    R4R_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    R4R_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, R4R_ENODEV, "conv_pool_tc: cuTensorMapEncodeTiled is not available in this driver");
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  R4R_REQUIRE(nslots >= 3 && lag >= 1, R4R_EUNSUP, "conv_pool_tc: E=%d F=%d leaves no room for the A ring next to the filter bank", E, F);
-  const int slot_bytes = CPS * RA * 16;
-  const size_t smem_bytes = (size_t)(ctl_bytes + b_bytes + (long long)nslots * slot_bytes);
+  CUtensorMap tmap;
+  {
+    const cuuint64_t gdim[2] = {(cuuint64_t)Epad, (cuuint64_t)V + 1};
+    const cuuint64_t gstride[1] = {(cuuint64_t)Epad * 2};
+    const cuuint32_t box[2] = {64, 1};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(&tmap, dtype == R4R_DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                              const_cast<void*>(shadow), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    R4R_REQUIRE(r == CUDA_SUCCESS, R4R_EINVAL, "conv_pool_tc: cuTensorMapEncodeTiled failed (%d) for V=%lld Epad=%d", (int)r, (long long)V, Epad);
+  }
 
   Params P;
   P.shadow = static_cast<const uint8_t*>(shadow);
@@ -809,11 +972,16 @@ static int conv_pool_tc_launch(const void* shadow, int64_t V, int Epad, int E, i
   P.N = N; P.T = T; P.Kc = pl.Kc; P.F = F; P.Npad = pl.Npad;
   P.wpack = static_cast<const uint8_t*>(wpack);
   P.bias = conv_b; P.pooled = pooled; P.argmax = argmax;
-  P.fmt = dtype; P.nslots = nslots; P.slot_bytes = slot_bytes;
+  P.fmt = dtype; P.nslots = nslots; P.slot_bytes = SLAB_BYTES;
+  {
+    const int spt = (pl.Kc + CPS - 1) / CPS;
+    P.tma_slabs = (2 * spt + 4) / 5;                        // 2 of 5 slabs at E = 300; every slab of narrow rows (spt <= 2: 1 of 1, 1 of 2)
+    const char* e = getenv("R4R_CONV_TMA_SLABS");           // tuning override
+    if (e && *e && atoi(e) >= 0) P.tma_slabs = atoi(e) < spt ? atoi(e) : spt;
+  }
   P.prof = g_prof;
   P.doc_len = doc_len;
   P.doc_order = doc_order;
-  P.lag = lag;
 
   R4R_CUDA(cudaFuncSetAttribute(conv_pool_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   long long nclusters = sm_count / 2;
@@ -824,7 +992,7 @@ static int conv_pool_tc_launch(const void* shadow, int64_t V, int Epad, int E, i
     if (want >= 1 && want < nclusters) nclusters = want;
   }
   if (nclusters > N) nclusters = N;
-  conv_pool_tc_kernel<<<(unsigned)(2 * nclusters), NUM_THREADS, smem_bytes, as_stream(stream)>>>(P);
+  conv_pool_tc_kernel<<<(unsigned)(2 * nclusters), NUM_THREADS, smem_bytes, as_stream(stream)>>>(P, tmap);
   R4R_CHECK_LAUNCH("conv_pool_tc");
   return 0;
 }

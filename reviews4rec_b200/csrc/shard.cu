@@ -229,7 +229,7 @@ inline unsigned grid_of(int64_t items, int per_block, int cap_blocks = 148 * 8) 
 
 extern "C" int r4r_shard_mark(const int64_t* idx, int64_t n, int64_t V, int32_t* flags, void* stream) {
   // flags: >= ceil(V/32) zeroed 32-bit words used as a bitmap (bit id % 32 of word id / 32)
-  R4R_REQUIRE(idx && flags, R4R_EINVAL, "shard_mark: null pointer");
+  R4R_REQUIRE(flags && (n == 0 || idx), R4R_EINVAL, "shard_mark: null pointer");
   R4R_REQUIRE(n >= 0 && V > 0, R4R_EINVAL, "shard_mark: bad sizes");
   if (n == 0) return 0;
   const int64_t bits = V < MARK_BITS ? V : MARK_BITS;
@@ -261,7 +261,7 @@ extern "C" int r4r_shard_plan(int32_t* flags, int64_t V, int P, int64_t cap, int
 
 extern "C" int r4r_shard_bucket(const int64_t* ids, int64_t n, int64_t R, int P, int64_t cap, int64_t* req, int64_t* pos,
                                 void* stream) {
-  R4R_REQUIRE(ids && req && pos, R4R_EINVAL, "shard_bucket: null pointer");
+  R4R_REQUIRE(req && (n == 0 || (ids && pos)), R4R_EINVAL, "shard_bucket: null pointer");
   R4R_REQUIRE(n >= 0 && R > 0 && P >= 1 && P <= 16 && cap >= n, R4R_EINVAL,
               "shard_bucket: need 1 <= P <= 16 and cap >= n (n=%lld cap=%lld)", (long long)n, (long long)cap);
   R4R_CUDA(cudaMemsetAsync(req, 0, (size_t)P * (size_t)(1 + cap) * sizeof(int64_t), as_stream(stream)));

@@ -408,7 +408,8 @@ class _Linear(torch.autograd.Function):
         n, in_f = x.shape
         out_f = W.shape[0]
         y = torch.empty(n, out_f, device=x.device, dtype=torch.float32)
-        call("r4r_linear_fwd", _p(x), _p(W), _p(b), n, in_f, out_f, _p(y), _stream())
+        if n:
+            call("r4r_linear_fwd", _p(x), _p(W), _p(b), n, in_f, out_f, _p(y), _stream())
         ctx.save_for_backward(x, W)
         ctx.has_bias = b is not None
         return y
@@ -422,7 +423,8 @@ class _Linear(torch.autograd.Function):
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         dW = zeros_f32(W.shape, x.device) if ctx.needs_input_grad[1] else None
         db = zeros_f32((out_f,), x.device) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
-        call("r4r_linear_bwd", _p(x), _p(W), _p(gy), n, in_f, out_f, _p(dx), _p(dW), _p(db), _stream())
+        if n:
+            call("r4r_linear_bwd", _p(x), _p(W), _p(gy), n, in_f, out_f, _p(dx), _p(dW), _p(db), _stream())
         return dx, dW, db
 
 
@@ -442,7 +444,8 @@ class _FM(torch.autograd.Function):
         n, nf = x.shape
         k = V.shape[1]
         out = torch.empty(n, device=x.device, dtype=torch.float32)
-        call("r4r_fm_fwd", _p(x), _p(V), _p(lin_w), _p(lin_b), n, nf, k, _p(out), _stream())
+        if n:
+            call("r4r_fm_fwd", _p(x), _p(V), _p(lin_w), _p(lin_b), n, nf, k, _p(out), _stream())
         ctx.save_for_backward(x, V, lin_w)
         return out
 
@@ -455,7 +458,8 @@ class _FM(torch.autograd.Function):
         dV = zeros_f32(V.shape, x.device)
         dw = zeros_f32(lin_w.shape, x.device)
         db = zeros_f32((1,), x.device)
-        call("r4r_fm_bwd", _p(x), _p(V), _p(lin_w), _p(_f32c(gout)), n, nf, k, _p(dx), _p(dV), _p(dw), _p(db), _stream())
+        if n:
+            call("r4r_fm_bwd", _p(x), _p(V), _p(lin_w), _p(_f32c(gout)), n, nf, k, _p(dx), _p(dV), _p(dw), _p(db), _stream())
         return dx, dV, dw, db
 
 
@@ -472,7 +476,8 @@ class _MSE(torch.autograd.Function):
         shape = out.shape
         o, t = _f32c(out).reshape(-1), _f32c(y.expand_as(out)).reshape(-1)
         se = torch.empty_like(o)
-        call("r4r_mse_fwd", _p(o), _p(t), o.numel(), _p(se), _p(None), _stream())
+        if o.numel():
+            call("r4r_mse_fwd", _p(o), _p(t), o.numel(), _p(se), _p(None), _stream())
         ctx.save_for_backward(o, t)
         ctx.shape = shape
         return se.reshape(shape)
@@ -481,7 +486,8 @@ class _MSE(torch.autograd.Function):
     def backward(ctx, gse):
         o, t = ctx.saved_tensors
         g = torch.empty_like(o)
-        call("r4r_mse_bwd", _p(o), _p(t), _p(_f32c(gse).reshape(-1)), o.numel(), _p(g), _stream())
+        if o.numel():
+            call("r4r_mse_bwd", _p(o), _p(t), _p(_f32c(gse).reshape(-1)), o.numel(), _p(g), _stream())
         return g.reshape(ctx.shape), None
 
 
@@ -498,7 +504,8 @@ class _RowsGather(torch.autograd.Function):
         L = 1 if table.dim() == 1 else table.shape[1]
         n = ids.numel()
         out = torch.empty((n,) if table.dim() == 1 else (n, L), device=table.device, dtype=torch.float32)
-        call("r4r_rows_gather", _p(table), table.shape[0], L, _p(ids), n, _p(out), _stream())
+        if n:
+            call("r4r_rows_gather", _p(table), table.shape[0], L, _p(ids), n, _p(out), _stream())
         ctx.save_for_backward(ids)
         ctx.tshape = tuple(table.shape)
         return out.reshape(*ids.shape) if table.dim() == 1 else out.reshape(*ids.shape, L)
@@ -509,7 +516,8 @@ class _RowsGather(torch.autograd.Function):
         L = 1 if len(ctx.tshape) == 1 else ctx.tshape[1]
         # dense gradient, as nn.Embedding(sparse=False) / Tensor.gather produce (SURVEY.md finding 5)
         gtable = torch.zeros(ctx.tshape, device=gout.device, dtype=torch.float32)
-        call("r4r_rows_scatter_add", _p(_f32c(gout)), _p(ids), ids.numel(), L, _p(gtable), ctx.tshape[0], _stream())
+        if ids.numel():
+            call("r4r_rows_scatter_add", _p(_f32c(gout)), _p(ids), ids.numel(), L, _p(gtable), ctx.tshape[0], _stream())
         return gtable, None
 
 

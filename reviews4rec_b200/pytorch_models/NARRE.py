@@ -54,15 +54,16 @@ class NARRE(nn.Module):
         n = user_id.numel()
         R_u, W_u = user_reviews.shape[-2], user_reviews.shape[-1]
         R_i, W_i = item_reviews.shape[-2], item_reviews.shape[-1]
-        users_who_reviewed = users_who_reviewed.reshape(n, -1)
-        reviewed_items = reviewed_items.reshape(n, -1)
+        users_who_reviewed = users_who_reviewed.reshape(n, users_who_reviewed.shape[-1])     # explicit widths: n may be 0
+        reviewed_items = reviewed_items.reshape(n, reviewed_items.shape[-1])
         user_id, item_id = user_id.reshape(-1), item_id.reshape(-1)
         ub = ops.rows_gather(self.user_bias, user_id)
         ib = ops.rows_gather(self.item_bias, item_id)
         # every review is its own conv document: [n*R, W] token ids (NARRE.py:91-104)
         user_docs, item_docs = self.word2vec.many(*self.word_inputs(data))
-        user = self.user_conv(user_docs).view(n, R_u, -1)
-        item = self.item_conv(item_docs).view(n, R_i, -1)
+        L = self.hyper_params["latent_size"]
+        user = self.user_conv(user_docs).view(n, R_u, L)
+        item = self.item_conv(item_docs).view(n, R_i, L)
         user = self.attention(user, self.item_embedding(reviewed_items), self.attention_scorer_user)
         item = self.attention(item, self.user_embedding(users_who_reviewed), self.attention_scorer_item)
         user = user + self.dropout(self.user_embedding(user_id))

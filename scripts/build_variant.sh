@@ -6,7 +6,7 @@ name=$1; shift
 cd "$(dirname "$0")/../reviews4rec_b200/csrc"
 out=../../scripts/_variants; mkdir -p $out/obj_$name
 ARCH="-gencode arch=compute_100a,code=sm_100a"
-for f in api gather conv_simt conv_tc wgrad head adam shard docplan docs dgrad; do
+for f in api gather conv_simt conv_tc wgrad head head_fused adam shard docplan docs dgrad; do
   if [ -f $f.cu ]; then nvcc -O3 -std=c++17 -lineinfo $ARCH -Xcompiler -fPIC "$@" -c $f.cu -o $out/obj_$name/$f.o & fi
 done
 wait

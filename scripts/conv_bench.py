@@ -69,5 +69,6 @@ if os.environ.get("CONV_PROF"):
     v = buf.tolist()
     for r in (0, 1):
         print("rank%d epilogue: total %d  wait_tmem_full %d  bar %d  xchg %d" % (r, *v[r * 16: r * 16 + 4]))
-        print("rank%d producer: total %d  wait_empty %d  wait_copies+publish %d" % (r, *v[r * 16 + 4: r * 16 + 7]))
+        print("rank%d tma team: total %d  wait_empty %d  tma_issue %d" % (r, *v[r * 16 + 4: r * 16 + 7]))
+        print("rank%d cp.async team: total %d  wait_empty %d  wait_copies+publish %d" % (r, *v[r * 16 + 12: r * 16 + 15]))
     print("mma: total %d  wait_tmem_empty %d  wait_full %d" % tuple(v[8:11]))

@@ -1,5 +1,5 @@
 // gather4_shift_test.cu -- micro-experiment for the planned TMA producer of conv_pool_tc (NOT part of the product,
-// never run yet: written offline at the end of round 1).
+// written offline at the end of round 1, first run in round 2: see scripts/experiments/README.md).
 //
 // Question: can the conv's three window rows be read from ONE staged tile when the tile is filled by
 // cp.async.bulk.tensor ... tile::gather4 into the canonical K-major SWIZZLE_128B layout, by advancing the UMMA
@@ -34,9 +34,11 @@ __global__ void __launch_bounds__(128, 1) test_kernel(const __grid_constant__ CU
   uint8_t* b_sm = smem + 17 * 1024;                       // B: 8 chunks x 16 rows x 16 B, no swizzle, chunk-major
   __shared__ unsigned long long bar_tma, bar_mma;
   __shared__ uint32_t tmem_base;
+  __shared__ int timed_out;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
+    timed_out = 0;
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar_tma)));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar_mma)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -65,11 +67,12 @@ __global__ void __launch_bounds__(128, 1) test_kernel(const __grid_constant__ CU
           :: "r"(smem_u32(a_sm + q * 512)), "l"(&tmap), "r"(smem_u32(&bar_tma)), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
           : "memory");
     }
-    // wait for the rows
+    // wait for the rows (bounded: a TMA that never completes must not hang the GPU)
     uint32_t done = 0;
-    while (!done)
+    for (long long spin = 0; !done && spin < (1LL << 22); ++spin)
       asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                    : "=r"(done) : "r"(smem_u32(&bar_tma)) : "memory");
+    if (!done) { out[0] = -12345.0f; timed_out = 1; }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // instruction descriptor: D f32, A/B f16, K-major both, N, M = 128
     const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -90,10 +93,10 @@ __global__ void __launch_bounds__(128, 1) test_kernel(const __grid_constant__ CU
     }
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&bar_mma)) : "memory");
   }
-  // everybody waits for the MMAs
+  // everybody waits for the MMAs (bounded)
   {
     uint32_t done = 0;
-    while (!done)
+    for (long long spin = 0; !done && spin < (1LL << 24); ++spin)
       asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                    : "=r"(done) : "r"(smem_u32(&bar_mma)) : "memory");
   }

@@ -48,17 +48,19 @@ def main():
         for data, y in golden_batches(z, dims, "cuda"):
             n_tot += int(y.shape[0])
             d, yy = S.shard_batch(data, y, rank, world)
-            # local means -> global-batch mean after the rank average: weight by B_local * P / B_global
-            wgt = float(yy.shape[0]) * world / float(y.shape[0])
+            # local SUMS scaled by P / B_global -> global-batch mean after the rank average (a rank's slice may be
+            # empty when the batch is smaller than the world: sums stay well defined, means would be NaN)
+            wgt = float(world) / float(y.shape[0])
             if is_tn:
                 # restated step (train.transnet_step) with rank-averaged replicated gradients
                 src, sfm, tgt = [list(x) for x in __import__("reviews4rec_b200.train", fromlist=["x"])._transnet_param_groups(model, hp)]
                 out = model(d)
-                lt, lx = crit(out[1], yy) * wgt, out[2] * wgt
+                lt = crit(out[1], yy, return_mean=False).sum() * wgt
+                lx = ((model.source.ir - model.target.ir) ** 2).sum() * wgt       # out[2] = its local mean (TransNet.py:118-122)
                 se = crit(out[0], yy, return_mean=False)
                 g_t = torch.autograd.grad(lt, tgt, retain_graph=True, allow_unused=True)
                 g_s = torch.autograd.grad(lx, src, retain_graph=True, allow_unused=True)
-                g_f = torch.autograd.grad(torch.mean(se) * wgt, sfm, allow_unused=True)
+                g_f = torch.autograd.grad(se.sum() * wgt, sfm, allow_unused=True)
                 for params, grads, o in ((tgt, g_t, opt[2]), (src, g_s, opt[0]), (sfm, g_f, opt[1])):
                     for p, g in zip(params, grads):
                         p.grad = g
@@ -72,7 +74,7 @@ def main():
                 out = model(d)
                 se = crit(out, yy, return_mean=False)
                 se_sum += se.detach().double().sum()
-                (torch.mean(se) * wgt).backward()
+                (se.sum() * wgt).backward()
                 S.allreduce_dense_grads(model)
                 opt.step()
         dist.all_reduce(se_sum)

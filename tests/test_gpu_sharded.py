@@ -210,3 +210,29 @@ def test_two_rank_training_matches_single_process_reference(transport):
            "--master-port", str(29600 + os.getpid() % 300), os.path.join(ROOT, "tests", "dist_parity.py"), "--transport", transport]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=200, cwd=ROOT)
     assert res.returncode == 0 and "DIST_PARITY_OK" in res.stdout, "\n".join(l for l in (res.stdout + res.stderr).splitlines() if "Error" in l or "error" in l or "assert" in l or "dist_parity" in l)[-3000:]
+
+
+@pytest.mark.parametrize("sharded_tables", [False, True])
+@pytest.mark.parametrize("mt", ["deepconn", "deepconn++", "NARRE", "transnet++", "MF_dot"])
+def test_empty_local_batch(S, mt, sharded_tables):
+    """A rank's slice of a small global batch can be empty (5 ratings over 8 ranks): forward and backward must run
+    (the collectives of the sharded tables still have to be entered) and leave zero gradients."""
+    import reviews4rec_b200 as R
+    from tests.test_gpu_models import build
+    z, dims = load_golden(mt)
+    model, hp = build(mt, z, dims, mode="f16")
+    if sharded_tables:
+        S.shard_model(model, S.Transport())
+    model.train()
+    data, y = golden_batches(z, dims, "cuda")[0]
+    data = [None if d is None else d[:0].contiguous() for d in data]
+    out = model(data)
+    outs = out if isinstance(out, list) else [out]
+    assert tuple(outs[0].shape) == (0,)
+    loss = R.MSELoss(hp)(outs[0], y[:0], return_mean=False).sum()
+    if mt.startswith("transnet"):
+        loss = loss + R.MSELoss(hp)(outs[1], y[:0], return_mean=False).sum()
+    loss.backward()
+    for n, p in model.named_parameters():
+        if p.grad is not None:
+            assert float(p.grad.abs().max()) == 0.0, n
