@@ -468,6 +468,86 @@ def fm(x, V, lin_w, lin_b) -> torch.Tensor:
     return _FM.apply(x, V, lin_w, lin_b).unsqueeze(1)
 
 
+# ------------------------------------------------------------------------------------ fused DeepCoNN head (K3)
+HEAD_MAX_L, HEAD_MAX_F, HEAD_MAX_K = 32, 128, 16
+
+
+def _vp_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))(*[(t.data_ptr() if t is not None else 0) for t in tensors])
+    return arr, ctypes.cast(arr, ctypes.c_void_p)
+
+
+class _DeepConnHead(torch.autograd.Function):
+    """fc_u / fc_i (+ dropout) -> cat -> FM + global bias (head 0) or final MLP + biases (head 1) -> rating [-> squared
+    error], one kernel forward, one backward (r4r_deepconn_head_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, pu, pi, fuw, fub, fiw, fib, fmV, fmw, fmb, w0, b0, w3, b3, ub, ib, gb, y, head, p, seed, step, masks, se_sum):
+        _need_cuda(pu, pi, fuw, fiw, gb)
+        f = lambda t: None if t is None else _f32c(t)
+        pu, pi, fuw, fub, fiw, fib, gb = f(pu), f(pi), f(fuw), f(fub), f(fiw), f(fib), f(gb)
+        fmV, fmw, fmb, w0, b0, w3, b3, ub, ib, y = f(fmV), f(fmw), f(fmb), f(w0), f(b0), f(w3), f(b3), f(ub), f(ib), f(y)
+        N, F = pu.shape
+        L = fuw.shape[0]
+        K = fmV.shape[1] if head == 0 else 0
+        dev = pu.device
+        rating = torch.empty(N, device=dev, dtype=torch.float32)
+        se = torch.empty(N, device=dev, dtype=torch.float32) if y is not None else None
+        cat = torch.empty(N, 2 * L, device=dev, dtype=torch.float32)
+        hid = torch.empty(N, L, device=dev, dtype=torch.float32) if head == 1 else None
+        keep = torch.empty(N, 3, device=dev, dtype=torch.int32)
+        w3f = None if w3 is None else w3.reshape(-1)
+        ptrs = [pu, pi, fuw, fiw, fub, fib, fmV, None if fmw is None else fmw.reshape(-1), fmb, w0, b0, w3f, b3, ub, ib, gb, y,
+                masks, step, rating, se, se_sum if y is not None else None, cat, hid, keep]
+        keepalive, vp = _vp_array(ptrs)
+        call("r4r_deepconn_head_fwd", vp, N, F, L, K, head, float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, _stream())
+        ctx.ptrs, ctx.dims = ptrs, (N, F, L, K, head, float(p))
+        ctx.shapes = [None if t is None else tuple(t.shape) for t in (fuw, fub, fiw, fib, fmV, fmw, fmb, w0, b0, w3, b3)]
+        return (rating, se) if y is not None else (rating, rating.new_zeros(0))
+
+    @staticmethod
+    def backward(ctx, g_rating, g_se):
+        N, F, L, K, head, p = ctx.dims
+        ptrs = ctx.ptrs
+        dev = ptrs[0].device
+        has_se = ptrs[16] is not None and g_se is not None and g_se.numel() == N
+        g_rating = None if g_rating is None else _f32c(g_rating)
+        g_se = _f32c(g_se) if has_se else None
+        sh = ctx.shapes
+        z = lambda shape: None if shape is None else zeros_f32(shape, dev)
+        dpu, dpi = torch.empty(N, F, device=dev), torch.empty(N, F, device=dev)
+        dfuw, dfub, dfiw, dfib = z(sh[0]), z(sh[1]), z(sh[2]), z(sh[3])
+        dV, dfmw, dfmb, dw0, db0, dw3, db3 = z(sh[4]), z(sh[5]), z(sh[6]), z(sh[7]), z(sh[8]), z(sh[9]), z(sh[10])
+        dub = torch.empty(N, device=dev) if head == 1 else None
+        dib = torch.empty(N, device=dev) if head == 1 else None
+        dg = zeros_f32((1,), dev)
+        if N:
+            gp = [g_rating, g_se, dpu, dpi, dfuw, dfiw, dfub, dfib, dV, dfmw, dfmb, dw0, db0, dw3, db3, dub, dib, dg]
+            ka1, vp1 = _vp_array(ptrs)
+            ka2, vp2 = _vp_array(gp)
+            call("r4r_deepconn_head_bwd", vp1, vp2, N, F, L, K, head, p, _stream())
+        return (dpu, dpi, dfuw, dfub, dfiw, dfib, dV, dfmw, dfmb, dw0, db0, dw3, db3, dub, dib, dg, None,
+                None, None, None, None, None, None)
+
+
+def deepconn_head(pooled_u, pooled_i, fc_u, fc_i, head, fm=None, final=None, ub=None, ib=None, global_bias=None, y=None,
+                  p=0.0, seed=0, step=None, masks=None, se_sum=None):
+    """Fused DeepCoNN head.  ``fc_u`` / ``fc_i`` = (weight [L,F], bias [L]); ``fm`` = (V [2L,K], lin.weight [1,2L], lin.bias [1])
+    for head 0; ``final`` = (final.0.weight [L,2L], final.0.bias, final.3.weight [1,L], final.3.bias) and the gathered bias
+    values ``ub`` / ``ib`` [N] for head 1.  Returns (rating [N], se [N] or None).  ``p`` = dropout probability of this call
+    (0 in eval mode), ``masks`` = uint8 keep masks [N, 3L] (tests), ``step`` = int32 device counter of the Philox stream
+    (advanced by the backward kernel), ``se_sum`` = device scalar the batch's squared-error sum is added to."""
+    fmV, fmw, fmb = fm if fm is not None else (None, None, None)
+    w0, b0, w3, b3 = final if final is not None else (None, None, None, None)
+    rating, se = _DeepConnHead.apply(pooled_u, pooled_i, fc_u[0], fc_u[1], fc_i[0], fc_i[1], fmV, fmw, fmb, w0, b0, w3, b3, ub, ib,
+                                     global_bias, y, int(head), float(p), int(seed), step, masks, se_sum)
+    return rating, (se if y is not None else None)
+
+
+def deepconn_head_supported(L, F, K):
+    return 0 < L <= HEAD_MAX_L and 0 < F <= HEAD_MAX_F and 0 <= K <= HEAD_MAX_K
+
+
 # ------------------------------------------------------------------------------------ MSE
 class _MSE(torch.autograd.Function):
     @staticmethod

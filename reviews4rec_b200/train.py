@@ -191,10 +191,16 @@ class CapturedStep:
                 self.se_sum += se.sum()
                 out = None
             else:
-                out = model(data)
-                se = criterion(out, y, return_mean=False)
-                self.se_sum += se.detach().sum()
-                torch.mean(se).backward()
+                if hasattr(model, "forward_with_loss"):
+                    # fused head: rating, squared error and its batch sum come out of one kernel (loss.py:7-11 folded in)
+                    out, se = model.forward_with_loss(data, y, self.se_sum)
+                    # mean over the batch: the upstream gradient 1/N of every se[n] (one fill, no reduction kernels)
+                    se.backward(torch.full_like(se, 1.0 / max(1, se.numel())))
+                else:
+                    out = model(data)
+                    se = criterion(out, y, return_mean=False)
+                    self.se_sum += se.detach().sum()
+                    torch.mean(se).backward()
                 if group is not None:
                     # replicated parameters: mean over ranks; row-sharded tables already received their
                     # rows' gradients from every rank inside the backward (sharded.py)
