@@ -11,6 +11,8 @@
 // the reference's vocabulary (50,001 x 300 x 4 B = 60 MB < 126 MB L2), so this kernel is bound by
 // L2 gather bandwidth, not HBM: N*F*3 row reads of 4E bytes.
 #include "common.cuh"
+#include <stdlib.h>
+#include <type_traits>
 
 namespace {
 constexpr int THREADS = 256;

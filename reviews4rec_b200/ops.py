@@ -347,6 +347,7 @@ class _ConvPool(torch.autograd.Function):
     def forward(ctx, idx, table, conv_w, conv_b, mode, shadow):
         # the reference freezes the word table (DeepCoNN.py:15): table.requires_grad is the opt-in extension of
         # SURVEY.md 8f-3 (hyper_params['train_word_table']), served by r4r_conv_dgrad_scatter in backward
+        ctx.set_materialize_grads(False)                # no zero-filled gradient for the (integer) arg-max output
         ctx.table_grad = table is not None and table.requires_grad
         ctx.conv_w = conv_w.detach() if ctx.table_grad else None
         if isinstance(idx, RaggedIdx):
@@ -364,6 +365,8 @@ class _ConvPool(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gpooled, _gargmax):
         idx, table, argmax, pooled = ctx.saved_tensors
+        if gpooled is None:
+            gpooled = torch.zeros_like(pooled)
         F, _, _, E = ctx.wshape
         rg = ctx.ragged
         N, T = (int(rg.shape[0]), int(rg.shape[1])) if rg is not None else idx.shape
@@ -484,6 +487,7 @@ class _DeepConnHead(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pu, pi, fuw, fub, fiw, fib, fmV, fmw, fmb, w0, b0, w3, b3, ub, ib, gb, y, head, p, seed, step, masks, se_sum):
         _need_cuda(pu, pi, fuw, fiw, gb)
+        ctx.set_materialize_grads(False)                # an unused output (rating when the loss is fused, or se) costs no zero fill
         f = lambda t: None if t is None else _f32c(t)
         pu, pi, fuw, fub, fiw, fib, gb = f(pu), f(pi), f(fuw), f(fub), f(fiw), f(fib), f(gb)
         fmV, fmw, fmb, w0, b0, w3, b3, ub, ib, y = f(fmV), f(fmw), f(fmb), f(w0), f(b0), f(w3), f(b3), f(ub), f(ib), f(y)
@@ -511,6 +515,8 @@ class _DeepConnHead(torch.autograd.Function):
         ptrs = ctx.ptrs
         dev = ptrs[0].device
         has_se = ptrs[16] is not None and g_se is not None and g_se.numel() == N
+        if g_rating is None and not has_se:
+            g_rating = torch.zeros(N, device=dev, dtype=torch.float32)
         g_rating = None if g_rating is None else _f32c(g_rating)
         g_se = _f32c(g_se) if has_se else None
         sh = ctx.shapes

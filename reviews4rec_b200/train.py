@@ -169,6 +169,8 @@ class CapturedStep:
             model(data)             # eager pass: builds the shadow word table and lazy kernel attributes outside the graph
         model.zero_grad(set_to_none=True)
         side = torch.cuda.Stream(device=dev) if words is not None else None
+        # d(mean se)/d se[n] = 1/N, as a constant made once outside the graph (no fill kernel per replay)
+        self._gse = torch.full((int(y.numel()),), 1.0 / max(1, int(y.numel())), device=dev, dtype=torch.float32)
         self.graph = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
         from . import _lib, ops
@@ -194,8 +196,8 @@ class CapturedStep:
                 if hasattr(model, "forward_with_loss"):
                     # fused head: rating, squared error and its batch sum come out of one kernel (loss.py:7-11 folded in)
                     out, se = model.forward_with_loss(data, y, self.se_sum)
-                    # mean over the batch: the upstream gradient 1/N of every se[n] (one fill, no reduction kernels)
-                    se.backward(torch.full_like(se, 1.0 / max(1, se.numel())))
+                    # mean over the batch: the upstream gradient 1/N of every se[n] (no reduction kernels)
+                    se.backward(self._gse.view_as(se))
                 else:
                     out = model(data)
                     se = criterion(out, y, return_mean=False)
