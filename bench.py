@@ -526,6 +526,24 @@ def run_b200(args):
         value_fp32 = {"value": B / (ms32 * 1e-3), "unit": "ratings/s", "ms_per_step": ms32, "steps": K32, "dtype": "f32",
                       "note": "conv on CUDA cores in fp32 (r4r_conv_pool_simt), everything else identical; device-resident inputs"}
         del steps32
+        # fp32-grade at tensor-core speed: the tcgen05 kernel selects each filter's arg-max window, r4r_conv_refine re-evaluates
+        # it in fp32 from the fp32 table and filters, and the weight gradient is the fp32 one (conv mode "f16r")
+        ops.set_conv_mode("f16r")
+        optr = make_optimizer(model, hp, capturable=True)
+        stepsr = [CapturedStep(model, criterion, optr, d, y, se32, None, 1.0) for d, y in res_batches]
+        Kr = max(3, min(K, 40))
+        for i in range(3):
+            stepsr[i % pool_n].replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(Kr):
+            stepsr[i % pool_n].replay()
+        e1.record()
+        torch.cuda.synchronize()
+        msr = e0.elapsed_time(e1) / Kr
+        value_fp32["refined"] = {"value": B / (msr * 1e-3), "unit": "ratings/s", "ms_per_step": msr, "steps": Kr, "conv_mode": "f16r",
+                                 "note": "tensor cores select the arg-max window, its value and the weight gradient are fp32 (r4r_conv_refine)"}
+        del stepsr
         ops.set_conv_mode(conv_mode)
     if world == 1 and not args.no_cpu_baseline:
         from oracle import r4r_oracle as O          # checker leg (precision + cpu_baseline), never the product path
@@ -537,7 +555,7 @@ def run_b200(args):
             ref = ref[0] if isinstance(ref, list) else ref
             precision = {}
             model.eval()
-            for m in ("exact", "f16", "bf16"):
+            for m in ("exact", "f16r", "f16", "bf16"):
                 ops.set_conv_mode(m)
                 out = model([None if x is None else x.to(dev) for x in sample])
                 out = (out[0] if isinstance(out, list) else out).cpu()

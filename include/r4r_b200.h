@@ -154,6 +154,11 @@ int r4r_conv_wgrad_argmax(const float* table, int64_t V, int E, const int64_t* i
                           const int32_t* argmax, const float* pooled, const float* gpooled, int F,
                           float* dW, float* db, void* stream);
 
+/* fp32 refinement of r4r_conv_pool_tc ("f16r" / "bf16r" modes): pooled[n,f] = relu(b[f] + the fp32 conv value of the window
+ * at argmax[n,f]), from the fp32 word table and filters (common_pytorch_models.py:29-31 at the selected position). */
+int r4r_conv_refine(const float* table, int64_t V, int E, const int64_t* idx, int64_t N, int T, const int32_t* argmax,
+                    const float* conv_w, const float* conv_b, int F, float* pooled, void* stream);
+
 /* Same gradient from the half-precision shadow rows the tensor-core forward read (f16 / bf16 modes):
  * it is the exact gradient of what r4r_conv_pool_tc computed and halves the gather traffic. */
 int r4r_conv_wgrad_argmax_h(const void* shadow, int64_t V, int Epad, int E, int dtype, const int64_t* idx, int64_t N,

@@ -41,6 +41,7 @@ SIGNATURES = {
     "r4r_conv_debug_profile": (c_int, [c_vp]),
     "r4r_conv_set_clusters": (c_int, [c_int]),
     "r4r_conv_wgrad_argmax": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
+    "r4r_conv_refine": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
     "r4r_conv_wgrad_argmax_h": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
     "r4r_conv_dgrad_scatter": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_i64, c_vp]),
     "r4r_linear_fwd": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp]),

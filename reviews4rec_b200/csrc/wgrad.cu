@@ -275,6 +275,68 @@ extern "C" int r4r_conv_wgrad_argmax(const float* table, int64_t V, int E, const
   return 0;
 }
 
+// ---- fp32 refinement of the tensor-core forward ("f16r" / "bf16r" conv modes).  The tcgen05 kernel has found, for every
+// (document, filter), the window with the largest conv value -- computed from half-precision operands.  This kernel
+// re-evaluates exactly that window in fp32 from the fp32 word table and the fp32 filters:
+//     pooled[n,f] = relu(b[f] + sum_j sum_e table[idx[n, a+j-2], e] * W[f,0,j,e])        a = argmax[n,f]
+// i.e. the reference's fp32 value of the selected window (common_pytorch_models.py:29-31).  It differs from the fp32
+// max-pool only where a second window lies within the half-precision rounding noise of the winner (then by less than
+// that noise).  Same gather pattern as the weight gradient: one warp per (document, filter), the filter in shared memory.
+constexpr int RTHREADS = 256;
+__global__ void __launch_bounds__(RTHREADS) conv_refine_kernel(const float* __restrict__ table, int64_t V, int E,
+                                                               const int64_t* __restrict__ idx, int64_t N, int T,
+                                                               const int32_t* __restrict__ argmax, const float* __restrict__ conv_w,
+                                                               const float* __restrict__ conv_b, int F, float* __restrict__ pooled) {
+  extern __shared__ __align__(16) float sw[];         // W[f, 0, :, :]: 3 x E floats
+  const int f = blockIdx.x;
+  for (int i = threadIdx.x; i < 3 * E; i += RTHREADS) sw[i] = __ldg(conv_w + (int64_t)f * 3 * E + i);
+  __syncthreads();
+  const float bias = __ldg(conv_b + f);
+  const int lane = threadIdx.x & 31;
+  const int e4 = E >> 2;
+  const int64_t warps = (int64_t)gridDim.y * (RTHREADS / 32);
+  for (int64_t n = (int64_t)blockIdx.y * (RTHREADS / 32) + (threadIdx.x >> 5); n < N; n += warps) {
+    const int a = __ldg(argmax + n * F + f);
+    float s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int pos = a + j - 2;
+      if (pos < 0 || pos >= T) continue;               // conv padding row (warp-uniform)
+      const int64_t tok = __ldg(idx + n * (int64_t)T + pos);
+      if (tok < 0 || tok >= V) __trap();
+      const float4* x = reinterpret_cast<const float4*>(table + tok * (int64_t)E);
+      const float4* w = reinterpret_cast<const float4*>(sw + j * E);
+      for (int c = lane; c < e4; c += 32) {
+        const float4 xv = __ldg(x + c), wv = w[c];
+        s = fmaf(xv.x, wv.x, s); s = fmaf(xv.y, wv.y, s); s = fmaf(xv.z, wv.z, s); s = fmaf(xv.w, wv.w, s);
+      }
+      for (int e = 4 * e4 + lane; e < E; e += 32) s = fmaf(__ldg(table + tok * (int64_t)E + e), sw[j * E + e], s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) {
+      const float o = s + bias;
+      pooled[n * F + f] = o > 0.0f ? o : 0.0f;
+    }
+  }
+}
+
+extern "C" int r4r_conv_refine(const float* table, int64_t V, int E, const int64_t* idx, int64_t N, int T, const int32_t* argmax,
+                               const float* conv_w, const float* conv_b, int F, float* pooled, void* stream) {
+  R4R_REQUIRE(table && idx && argmax && conv_w && conv_b && pooled, R4R_EINVAL, "conv_refine: null pointer");
+  R4R_REQUIRE(V > 0 && E > 0 && E <= 4096 && T > 0 && N >= 0 && F > 0, R4R_EINVAL, "conv_refine: bad sizes");
+  R4R_REQUIRE(E % 4 != 0 || reinterpret_cast<uintptr_t>(table) % 16 == 0, R4R_EINVAL, "conv_refine: table must be 16-byte aligned");
+  if (N == 0) return 0;
+  int64_t S = cdiv64(N, RTHREADS / 32);
+  const int64_t want = (148 * 8 * 4 + F - 1) / F;       // ~4 waves of 8 resident CTAs per SM over the F filters
+  if (S > want) S = want;
+  if (S < 1) S = 1;
+  dim3 grid((unsigned)F, (unsigned)S);
+  conv_refine_kernel<<<grid, RTHREADS, (size_t)3 * E * sizeof(float), as_stream(stream)>>>(table, V, (E % 4 == 0) ? E : E, idx, N, T, argmax, conv_w,
+                                                                                           conv_b, F, pooled);
+  R4R_CHECK_LAUNCH("conv_refine");
+  return 0;
+}
+
 static int conv_wgrad_h_launch(const void* shadow, int64_t V, int Epad, int E, int dtype, const int64_t* idx,
                                const int32_t* tok32, const int64_t* off, int64_t pad_id, int64_t N,
                                int T, const int32_t* argmax, const float* pooled, const float* gpooled, int F,

@@ -13,7 +13,7 @@ from . import _lib
 from ._lib import call
 
 NUM_FILTERS = 100          # common_pytorch_models.py:11
-_MODES = ("exact", "f16", "bf16")
+_MODES = ("exact", "f16", "bf16", "f16r", "bf16r")
 _conv_mode = os.environ.get("R4R_CONV_MODE", "f16")
 _doc_plan = os.environ.get("R4R_DOC_PLAN", "1") != "0"      # skip the repeated-padding tail of documents (exact)
 _PAIR_TILE = 256                                             # conv positions per CTA-pair tile of conv_pool_tc
@@ -62,7 +62,9 @@ def doc_lengths(idx: "torch.Tensor") -> "torch.Tensor":
 
 def set_conv_mode(mode: str) -> None:
     """'exact' = fp32 CUDA-core kernel (strict parity); 'f16' / 'bf16' = tcgen05 tensor-core kernel
-    reading a private half-precision shadow of the frozen word table (fp32 accumulation)."""
+    reading a private half-precision shadow of the frozen word table (fp32 accumulation); 'f16r' / 'bf16r' = the
+    tensor-core kernel only SELECTS each filter's arg-max window, whose value is then re-evaluated in fp32 from the
+    fp32 table and filters (r4r_conv_refine) and whose gradient is the fp32 one: fp32-grade results at tensor-core speed."""
     global _conv_mode
     if mode not in _MODES:
         raise ValueError("conv mode must be one of %s" % (_MODES,))
@@ -302,7 +304,7 @@ def conv_pool_forward(idx: torch.Tensor, table: torch.Tensor, conv_w: torch.Tens
     argmax = torch.empty(N, F, device=dev, dtype=torch.int32)
     used = None
     if N == 0:                                                   # empty batch: nothing to launch
-        if mode != "exact":
+        if mode in ("f16", "bf16"):
             shadow = shadow if shadow is not None else ShadowTable()
             used = (shadow.get(table, mode), shadow.epad, V)
         return (pooled, argmax, used) if want_shadow else (pooled, argmax)
@@ -312,6 +314,10 @@ def conv_pool_forward(idx: torch.Tensor, table: torch.Tensor, conv_w: torch.Tens
             call("r4r_conv_pool_simt", _p(table), V, E, _p(idx), N, T, _p(conv_w), _p(conv_b), F,
                  _p(pooled), _p(argmax), _p(keys), _stream())
     else:
+        refine = mode.endswith("r")
+        mode = mode[:-1] if refine else mode
+        if refine and (table is None or ragged is not None):
+            raise RuntimeError("the fp32-refined conv modes need the fp32 word table and padded ids")
         shadow = shadow if shadow is not None else ShadowTable()
         sh = shadow.get(table, mode)
         dt = _lib.R4R_DT_F16 if mode == "f16" else _lib.R4R_DT_BF16
@@ -339,6 +345,10 @@ def conv_pool_forward(idx: torch.Tensor, table: torch.Tensor, conv_w: torch.Tens
                 call("r4r_conv_pool_tc_ragged", _p(sh), V, shadow.epad, E, dt, _p(ragged.tokens), _p(ragged.offsets),
                      ragged.pad_id, N, T, _p(wpack), _p(conv_b), F, _p(pooled), _p(argmax), _p(doc_len), _p(doc_order), _stream())
         used = (sh, shadow.epad, V)
+        if refine:
+            # fp32 value of the selected window; the backward then is the fp32 gradient (used = None)
+            call("r4r_conv_refine", _p(table), V, E, _p(idx), N, T, _p(argmax), _p(conv_w), _p(conv_b), F, _p(pooled), _stream())
+            used = None
     return (pooled, argmax, used) if want_shadow else (pooled, argmax)
 
 
@@ -352,7 +362,7 @@ class _ConvPool(torch.autograd.Function):
         ctx.conv_w = conv_w.detach() if ctx.table_grad else None
         if isinstance(idx, RaggedIdx):
             idx = idx.reshape(-1, idx.shape[-1])
-            if mode == "exact" or not _ragged_native:
+            if mode == "exact" or mode.endswith("r") or not _ragged_native:
                 idx = idx.padded()
         pooled, argmax, used = conv_pool_forward(idx, table, conv_w, conv_b, mode, shadow, want_shadow=True)
         ctx.ragged = idx if isinstance(idx, RaggedIdx) else None

@@ -49,7 +49,7 @@ HP = {"model_type": "deepconn", "latent_size": 10, "word_embed_size": 300, "drop
       "total_items": 100_000, "lr": 0.002, "weight_decay": 1e-6, "input_length": 1000, "batch_size": B}
 # conv operand precision -> tolerance on pooled features / latent vectors, relative to the largest magnitude
 # (f16: 11-bit significands, bf16: 8-bit; fp32 accumulation in both)
-FEATURE_TOL = {"exact": 2e-5, "f16": 3e-4, "bf16": 2.4e-3}
+FEATURE_TOL = {"exact": 2e-5, "f16": 3e-4, "bf16": 2.4e-3, "f16r": 2e-5}
 
 
 def _cat(batches):
@@ -116,7 +116,7 @@ def _device_features(model, held):
 # ratings are ~4.2 +- 0.007 even after training (the reference xavier-initialises the word table, SURVEY.md finding 2,
 # so conv features stay small next to global_bias): 1e-4 relative alone would be a weak check, hence the error is
 # ALSO bounded relative to the spread of the ratings around their mean (the part the towers actually contribute)
-SPREAD_TOL = {"exact": 1e-3, "f16": 2e-2, "bf16": 1e-1}
+SPREAD_TOL = {"exact": 1e-3, "f16": 2e-2, "bf16": 1e-1, "f16r": 1e-3}
 REPORT = {}
 
 
@@ -149,7 +149,7 @@ def _save_report():
 GRAD_TOL = 1e-4          # per tensor, relative to its largest gradient entry (fast modes: vs the oracle on rounded operands)
 
 
-@pytest.mark.parametrize("mode", ["exact", "f16", "bf16"])
+@pytest.mark.parametrize("mode", ["exact", "f16", "bf16", "f16r"])
 def test_benchmarked_shape_120_adam_steps_and_parity_along_the_trajectory(world, mode):
     import reviews4rec_b200 as R
     from reviews4rec_b200 import ops
@@ -183,6 +183,11 @@ def test_benchmarked_shape_120_adam_steps_and_parity_along_the_trajectory(world,
             what = "oracle parameters after %d steps" % step
             feats = _device_features(model, world["held"])
             _check(feats, st, mode, what + " (vs fp32 oracle)")
+            if mode == "f16r":
+                # fp32-refined mode: the tensor cores only select the window, its value is re-evaluated in fp32 -- the features
+                # above already had to meet the fp32 ("exact") tolerances; the gradient follows the f16-selected windows, for
+                # which no oracle exists (see the module docstring on arg-max re-routing)
+                continue
             tight = st if mode == "exact" else st[mode]          # the oracle on this mode's rounded operands
             if mode != "exact":
                 _check(feats, tight, mode, what + " (vs oracle on rounded operands)", tol_as="exact")

@@ -339,3 +339,41 @@ def test_conv_pool_empty_batch(R, mode):
     out = ops.conv_pool(idx, table, w, b, mode=mode)
     out.sum().backward()
     assert float(w.grad.abs().max()) == 0.0 and float(b.grad.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("N,T,E,V", [(40, 600, 64, 90), (64, 1000, 300, 500), (9, 20, 12, 40)])
+def test_conv_refine_gives_the_fp32_value_of_the_selected_window(R, O, N, T, E, V):
+    """'f16r' mode: arg-max from the tensor-core kernel, value re-evaluated in fp32 (r4r_conv_refine).  The pooled features
+    must agree with the fp32 oracle far below the half-precision operand error, and the selected window must be (within
+    that error) a maximiser of the fp32 conv."""
+    from reviews4rec_b200 import ops
+    g = gen(21)
+    table = (torch.randn(V, E, generator=g) * 0.5)
+    w = (torch.randn(100, 1, 3, E, generator=g) * (1.0 / (3 * E) ** 0.5))
+    b = (torch.randn(100, generator=g) * 0.1)
+    idx = _ragged_docs(8, N, T, V)
+    pooled_ref, arg_ref = O.conv_pool(O.word_gather(table, idx), w, b)
+    p_r, a_r = ops.conv_pool_forward(idx.cuda(), table.cuda(), w.cuda(), b.cuda(), "f16r")
+    p_h, a_h = ops.conv_pool_forward(idx.cuda(), table.cuda(), w.cuda(), b.cuda(), "f16")
+    assert torch.equal(a_r, a_h)                                  # same selection
+    scale = float(pooled_ref.abs().max())
+    err_r = float((p_r.cpu() - pooled_ref).abs().max())
+    err_h = float((p_h.cpu() - pooled_ref).abs().max())
+    # where the tensor cores selected the oracle's window the value is the fp32 one; a different window (a near tie the
+    # half-precision operands resolved the other way) is below the fp32 maximum by less than the f16 operand error
+    live = pooled_ref > 0
+    same = (a_r.cpu().long() == torch.as_tensor(arg_ref).long()) & live
+    assert float(same.sum()) > 0.95 * float(live.sum())
+    assert float((p_r.cpu() - pooled_ref).abs()[same].max()) <= 2e-5 * scale + 1e-6
+    assert bool((p_r.cpu() <= pooled_ref + 2e-5 * scale).all())   # never above the true maximum
+    assert err_r <= err_h + 1e-6, (err_r, err_h)
+    mean_r = float((p_r.cpu() - pooled_ref).abs().mean()); mean_h = float((p_h.cpu() - pooled_ref).abs().mean())
+    assert mean_r < 0.1 * mean_h, (mean_r, mean_h)                # on average an order of magnitude closer than plain f16
+    # gradients: fp32 rows of the selected windows (the exact-mode weight-gradient kernel)
+    wc, bc = w.clone().cuda().requires_grad_(True), b.clone().cuda().requires_grad_(True)
+    out = ops.conv_pool(idx.cuda(), table.cuda(), wc, bc, mode="f16r")
+    gout = torch.randn(N, 100, generator=g).cuda()
+    out.backward(gout)
+    ref_w, ref_b = O.conv_wgrad_argmax(O.word_gather(table, idx), a_r.cpu().long(), gout.cpu(), p_r.cpu())
+    assert_close(wc.grad.cpu().reshape(ref_w.shape), ref_w, rtol=1e-4, atol=1e-5, msg="dW at the selected windows")
+    assert_close(bc.grad.cpu(), ref_b, rtol=1e-4, atol=1e-5, msg="db")
