@@ -344,7 +344,7 @@ def run_b200(args):
 
     # conv positions the launches actually process (documents cut to their informative prefix, exact)
     pos_sum, n_docs = 0, 0
-    plan_on = ops.get_doc_plan() and T + 2 > 256
+    plan_on = ops.get_doc_plan()
     for d, _ in res_batches:
         for j in doc_slots:
             idx = d[j] if isinstance(d[j], ops.RaggedIdx) else d[j].reshape(-1, T)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define R4R_ABI_VERSION 4
+#define R4R_ABI_VERSION 5
 
 #define R4R_EINVAL   (-1)   /* bad argument (null pointer, size out of supported range)          */
 #define R4R_EUNSUP   (-2)   /* shape outside what the sm_100a kernels were built for             */
@@ -91,18 +91,25 @@ int r4r_conv_pool_simt(const float* table, int64_t V, int E, const int64_t* idx,
  * (r4r_conv_wpack_bytes(E,F) bytes).  Re-run after every optimizer step that changes conv_w. */
 int64_t r4r_conv_wpack_bytes(int E, int F);
 int r4r_conv_pack_weights(const float* conv_w, int E, int F, void* wpack, int dtype, void* stream);
+/* `ws`: r4r_conv_stream_ws_bytes(N, T) bytes of device scratch per launch.  The launch first lays the documents of every
+ * persistent CTA pair end to end as one stream of conv windows (two zero rows between documents, shared by the window
+ * that closes one and the window that opens the next), so the tensor cores run over tiles of 256 CONSECUTIVE windows
+ * instead of rounding each document up to whole tiles; max / arg-max are taken per document over the windows it owns.
+ * Results are independent of the launch partition (bit-identical for any batch split / order). */
+int64_t r4r_conv_stream_ws_bytes(int64_t N, int T);
 int r4r_conv_pool_tc(const void* shadow, int64_t V, int Epad, int E, int dtype,
                      const int64_t* idx, int64_t N, int T,
                      const void* wpack, const float* conv_b, int F,
                      float* pooled, int32_t* argmax,
-                     const int32_t* doc_len, const int32_t* doc_order, void* stream);
+                     const int32_t* doc_len, const int32_t* doc_order, void* ws, void* stream);
 
 /* Work plan for r4r_conv_pool_tc (optional: pass NULL, NULL to process every row of every document).
  * The readers pad documents to T with one repeated token that is embedded like any other
  * (data.py:198-199, DeepCoNN.py:53-54); conv windows inside such a trailing run all produce the same
  * value and max_pool1d keeps the first, so a document whose rows s..T-1 are equal gives bit-identical
  * (pooled, argmax) when cut to doc_len = min(T, s+3) rows, with arg-max positions >= doc_len mapped
- * back by + (T - doc_len).  doc_order = documents by decreasing tile count (load balance).
+ * back by + (T - doc_len).  doc_order = documents by decreasing length in 256 classes of (T+2)/255 windows (load balance:
+ * the conv launch deals them to its CTA pairs in rounds of alternating direction).
  * The order is a stable sort (deterministic: no global atomics).  ws: r4r_doc_plan_ws_bytes(N, T) bytes of scratch. */
 int64_t r4r_doc_plan_ws_bytes(int64_t N, int T);
 int r4r_doc_plan(const int64_t* idx, int64_t N, int T, int32_t* doc_len, int32_t* doc_order, void* ws,
@@ -115,7 +122,7 @@ int r4r_conv_pool_tc_ragged(const void* shadow, int64_t V, int Epad, int E, int 
                             const int32_t* tokens, const int64_t* offsets, int64_t pad_id, int64_t N, int T,
                             const void* wpack, const float* conv_b, int F,
                             float* pooled, int32_t* argmax,
-                            const int32_t* doc_len, const int32_t* doc_order, void* stream);
+                            const int32_t* doc_len, const int32_t* doc_order, void* ws, void* stream);
 /* doc_len[n] = min(T, offsets[n+1] - offsets[n] + 3): the padding run starts where the stored tokens end */
 int r4r_doc_plan_ragged(const int64_t* offsets, int64_t N, int T, int32_t* doc_len, int32_t* doc_order, void* ws,
                         void* stream);

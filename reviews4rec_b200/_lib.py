@@ -32,10 +32,11 @@ SIGNATURES = {
     "r4r_conv_pool_simt": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
     "r4r_conv_wpack_bytes": (c_i64, [c_int, c_int]),
     "r4r_conv_pack_weights": (c_int, [c_vp, c_int, c_int, c_vp, c_int, c_vp]),
-    "r4r_conv_pool_tc": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "r4r_conv_stream_ws_bytes": (c_i64, [c_i64, c_int]),
+    "r4r_conv_pool_tc": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "r4r_doc_plan_ws_bytes": (c_i64, [c_i64, c_int]),
     "r4r_doc_plan": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
-    "r4r_conv_pool_tc_ragged": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "r4r_conv_pool_tc_ragged": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "r4r_doc_plan_ragged": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
     "r4r_conv_wgrad_argmax_h_ragged": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
     "r4r_conv_debug_profile": (c_int, [c_vp]),
@@ -72,14 +73,15 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn.argtypes = _args
 
 R4R_DT_F16, R4R_DT_BF16 = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 if lib.r4r_abi_version() != ABI_VERSION:
     raise ImportError("reviews4rec_b200: libr4r_b200.so ABI %d != expected %d -- rebuild" % (lib.r4r_abi_version(), ABI_VERSION))
 
 # number of kernel launches issued through this binding (bench.py reports it as gpu_launches)
 launch_count = 0
-_LAUNCHES_PER_CALL = {"r4r_conv_pool_simt": 2, "r4r_linear_bwd": 2, "r4r_shard_bucket": 2, "r4r_shard_plan": 2, "r4r_doc_plan": 3, "r4r_doc_plan_ragged": 3}
+_LAUNCHES_PER_CALL = {"r4r_conv_pool_simt": 2, "r4r_linear_bwd": 2, "r4r_shard_bucket": 2, "r4r_shard_plan": 2, "r4r_doc_plan": 3, "r4r_doc_plan_ragged": 3,
+                      "r4r_conv_pool_tc": 3, "r4r_conv_pool_tc_ragged": 3}
 
 
 def check(rc, name="r4r"):

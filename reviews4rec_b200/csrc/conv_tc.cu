@@ -253,10 +253,6 @@ struct Params {
   const uint8_t* shadow;     // [V][Epad] 2-byte elements
   long long row_bytes;       // Epad * 2
   long long V;
-  const long long* idx;      // [N][T] padded token ids, or NULL when the documents come ragged:
-  const int* tok32;          //   tokens of all documents back to back (those before each trailing padding run)
-  const long long* off;      //   [N+1] offsets into tok32; rows off[n+1]-off[n] .. T-1 of document n are pad_id
-  long long pad_id;
   long long N;
   int T;
   int Kc;                    // 16-byte chunks per window row = ceil(E/16)*2
@@ -271,37 +267,23 @@ struct Params {
   int slot_bytes;
   int tma_slabs;             // slabs 0 .. tma_slabs-1 of every tile are staged by TMA, the rest by cp.async
   unsigned long long* prof;  // diagnostics: per-role cycle counters of cluster 0 (r4r_conv_debug_profile), or NULL
-  const int* doc_len;        // [N] effective document lengths (r4r_doc_plan), or NULL = T for every document
-  const int* doc_order;      // [N] processing order (longest first), or NULL = identity
+  // the launch's window streams (stream_plan_kernel / stream_fill_kernel below), one per CTA pair
+  const int* stream;         // row u of cluster c at stream[c * stream_stride + u]: token id, or -1 = all-zero (conv padding) row
+  long long stream_stride;   // ints per cluster (a multiple of 4)
+  const int4* dlist;         // document i of cluster c at dlist[c * dlist_stride + i] = (document, effective length, first window, 0)
+  long long dlist_stride;
+  const int2* head;          // per cluster: (tiles of 256 windows, documents)
 };
 
-// Work item k of the launch -> (document, its effective length).  A document whose last rows repeat
-// one token (the reader's padding, data.py:198-199) is processed as if it ended three rows into that
-// run: all later windows would reproduce values already seen (see r4r_doc_plan in the header).
-__device__ __forceinline__ void work_item(const Params& P, long long k, long long& doc, int& Td) {
-  doc = P.doc_order ? (long long)__ldg(P.doc_order + k) : k;
-  Td = P.doc_len ? __ldg(P.doc_len + doc) : P.T;
-}
-// producer's view of a work item: also where the document's stored tokens are (ragged input)
-struct DocRef {
-  long long doc;
-  int Td, npt;
-  long long base;            // ragged: offset of the document's first token in tok32
-  int len;                   // ragged: number of stored tokens (rows len..T-1 are pad_id)
-};
-__device__ __forceinline__ int tiles_of(int Td);
-__device__ __forceinline__ DocRef doc_ref(const Params& P, long long k) {
-  DocRef d;
-  work_item(P, k, d.doc, d.Td);
-  d.npt = tiles_of(d.Td);
-  d.base = 0;
-  d.len = 0;
-  if (P.tok32) {
-    d.base = __ldg(P.off + d.doc);
-    d.len = (int)(__ldg(P.off + d.doc + 1) - d.base);
-  }
-  return d;
-}
+// The WINDOW STREAM of a CTA pair.  Its documents are laid end to end, each as two zero rows followed by its
+// (effective) rows; the two zero rows that open document i+1 also close document i:
+//     rows     z z a0 a1 .. aL-1 z z b0 b1 .. bM-1 z z ...
+// Window w covers rows w, w+1, w+2.  Document a (first row index o) owns windows o .. o+L+1 = its L+2 conv positions
+// (position p <-> window o + p), document b starts at window o + L + 2: every window belongs to exactly one document
+// and none straddles two documents' rows.  The pair's tensor cores therefore run over tiles of 256 CONSECUTIVE windows
+// of the stream -- a tile holds the end of one document and the start of the next -- instead of rounding every
+// document up to whole tiles (Amazon-shaped batches: 2.08 -> 1.59 tiles per document).  The epilogue takes the
+// max / arg-max per document over the window range it owns.
 __device__ __forceinline__ int tiles_of(int Td) { return (Td + 2 + 2 * TILE_M - 1) / (2 * TILE_M); }
 
 // ------------------------------------------------------------------------------------------
@@ -329,21 +311,26 @@ __device__ __forceinline__ uint32_t redux_min_u32(uint32_t v) {
 
 
 template <int EC>   // accumulator columns handled by one epilogue warp = Npad / 2
-__device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, uint32_t rank, int cluster_id, int nclusters,
-                                              int warp, int lane) {
+__device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, uint32_t rank, int cluster_id, int warp, int lane) {
   const int q = warp & 3, h = warp >> 2;
   const int row = q * 32 + lane;
   const uint32_t lane_base = (uint32_t)(q * 32) << 16;
   const uint32_t leader_tmem_empty0 = mapa(smem_u32(&ctl->tmem_empty[0]), 0);
-  uint32_t it = 0, ndoc = 0;
   const bool prof_on = P.prof != nullptr && cluster_id == 0;
   long long w_full = 0, w_bar = 0, w_xchg = 0, t_begin = clock64();
-  for (long long k = cluster_id; k < P.N; k += nclusters, ++ndoc) {
-    long long doc;
-    int Td;
-    work_item(P, k, doc, Td);
+  const int nd = __ldg(P.head + cluster_id).y;
+  const int4* dl = P.dlist + (long long)cluster_id * P.dlist_stride;
+  const int wrow0 = (int)rank * TILE_M + q * 32;          // first window of this warp inside a tile
+  int acquired = -1;                                      // last stream tile whose accumulator this warp has waited for
+  int4 e_next = nd > 0 ? __ldg(dl) : make_int4(0, 0, 0, 0);
+  for (int i = 0; i < nd; ++i) {
+    const int4 e = e_next;                                // (document, effective length, first window)
+    if (i + 1 < nd) e_next = __ldg(dl + i + 1);
+    const long long doc = e.x;
+    const int Td = e.y, o = e.z;
     const int npos = Td + 2;
-    const int npt = tiles_of(Td);
+    const int w_end = o + npos;                           // one past the document's last window
+    const int t0 = o >> 8, t1 = (w_end - 1) >> 8;         // stream tiles holding its windows
     // running maximum per filter column and the tile it came from (one byte per column, packed
     // four to a register)
     float best[EC];
@@ -352,49 +339,65 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
     for (int c = 0; c < EC; ++c) best[c] = -INFINITY;
 #pragma unroll
     for (int c = 0; c < EC / 4; ++c) btile[c] = 0u;
-    for (int pt = 0; pt < npt; ++pt, ++it) {
-      const uint32_t buf = it % NACC, ph = (it / NACC) & 1u;
-      TIMED_WAIT(w_full, mbar_wait(&ctl->tmem_full[buf], ph));
-      tc_fence_after();
-      const bool valid = (pt * 2 * TILE_M + (int)rank * TILE_M + row) < npos;
-      const uint32_t taddr = ctl->tmem_base + lane_base + buf * ACC_STRIDE + h * EC;
-      uint32_t tsh[4];
+    bool touched = false;                                 // warp-uniform: some row of this warp belongs to the document
+    for (int t = t0; t <= t1; ++t) {
+      const uint32_t buf = (uint32_t)t % NACC, ph = ((uint32_t)t / NACC) & 1u;
+      if (t > acquired) {
+        // every warp waits for every tile, also one it has no rows in: its release below must not run ahead of the
+        // tile's MMAs (the arrival counts of tmem_empty assume one arrival per warp per use of the buffer)
+        TIMED_WAIT(w_full, mbar_wait(&ctl->tmem_full[buf], ph));
+        tc_fence_after();
+        acquired = t;
+      }
+      const int wbase = t * 2 * TILE_M + wrow0;           // window of lane 0
+      if (wbase < w_end && wbase + 32 > o) {              // warp-uniform: the tcgen05.ld below are warp-collective
+        touched = true;
+        const int w = wbase + lane;
+        const bool valid = w >= o && w < w_end;
+        const uint32_t taddr = ctl->tmem_base + lane_base + buf * ACC_STRIDE + h * EC;
+        uint32_t tsh[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) tsh[k] = (uint32_t)pt << (8 * k);
+        for (int k = 0; k < 4; ++k) tsh[k] = (uint32_t)(t - t0) << (8 * k);
 #pragma unroll
-      for (int c0 = 0; c0 < EC; c0 += 16) {
-        uint32_t v[16];
-        if (c0 + 16 <= EC) {
-          tmem_ld16(taddr + c0, v);
-        } else {
-          uint32_t v8[8];
-          tmem_ld8(taddr + c0, v8);
+        for (int c0 = 0; c0 < EC; c0 += 16) {
+          uint32_t v[16];
+          if (c0 + 16 <= EC) {
+            tmem_ld16(taddr + c0, v);
+          } else {
+            uint32_t v8[8];
+            tmem_ld8(taddr + c0, v8);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) v[c] = v8[c];
-        }
-        tmem_ld_wait();
-        if (valid) {
+            for (int c = 0; c < 8; ++c) v[c] = v8[c];
+          }
+          tmem_ld_wait();
+          if (valid) {
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            if (c0 + c < EC) {
-              float x = __uint_as_float(v[c]);
-              if (x > best[c0 + c]) {
-                best[c0 + c] = x;
-                btile[(c0 + c) >> 2] = (btile[(c0 + c) >> 2] & ~(0xffu << (8 * (c & 3)))) | tsh[c & 3];
+            for (int c = 0; c < 16; ++c) {
+              if (c0 + c < EC) {
+                float x = __uint_as_float(v[c]);
+                if (x > best[c0 + c]) {
+                  best[c0 + c] = x;
+                  btile[(c0 + c) >> 2] = (btile[(c0 + c) >> 2] & ~(0xffu << (8 * (c & 3)))) | tsh[c & 3];
+                }
               }
             }
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + buf * 8u);
+      // the accumulator is released by the document that reaches the end of the tile (later documents start in later
+      // tiles), or by the pair's last document
+      if (w_end >= (t + 1) * 2 * TILE_M || i == nd - 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + buf * 8u);
+      }
     }
     // ---- per-document reduction over the warp's 32 rows: max value, smallest position on ties.
     // Two warp-wide reductions per column (redux.sync -> CREDUX): the maximum, then the smallest
     // key = tile << 5 | lane among the lanes that hold it (positions within one warp are ordered by
     // tile, then lane: same CTA rank and lane quarter).  Lane c % 32 keeps column c.
-    {
+    // (Measured alternative: one redux + a shared-memory atomicMin by the holders -- 0.417 instead of 0.334 ms per launch.)
+    if (touched) {
       float keep_v[(EC + 31) / 32];
       uint32_t keep_k[(EC + 31) / 32];
 #pragma unroll
@@ -405,14 +408,21 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
         if (lane == (c & 31)) { keep_v[c >> 5] = m; keep_k[c >> 5] = kmin; }
       }
 #pragma unroll
-      for (int i = 0; i < (EC + 31) / 32; ++i) {
-        const int c = lane + 32 * i;
+      for (int i2 = 0; i2 < (EC + 31) / 32; ++i2) {
+        const int c = lane + 32 * i2;
         if (c < EC) {
-          const float v = keep_v[i];
+          const float v = keep_v[i2];
+          // window -> position of the document: (t0 + tile) * 256 + rank * 128 + q * 32 + lane - o
           ctl->red_val[warp][c] = v;
           ctl->red_pos[warp][c] = v == -INFINITY ? 0x7fffffff
-                                                 : (int)(keep_k[i] >> 5) * 2 * TILE_M + (int)rank * TILE_M + q * 32 + (int)(keep_k[i] & 31u);
+                                                 : (t0 + (int)(keep_k[i2] >> 5)) * 2 * TILE_M + wrow0 + (int)(keep_k[i2] & 31u) - o;
         }
+      }
+    } else {
+#pragma unroll
+      for (int i2 = 0; i2 < (EC + 31) / 32; ++i2) {
+        const int c = lane + 32 * i2;
+        if (c < EC) { ctl->red_val[warp][c] = -INFINITY; ctl->red_pos[warp][c] = 0x7fffffff; }
       }
     }
     TIMED_WAIT(w_bar, asm volatile("bar.sync %0, 128;" :: "r"(1 + h) : "memory"));
@@ -431,7 +441,7 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
     if (col_thread) {
       // ---- merge the two CTAs' halves of the document through distributed shared memory
       const int f = h * EC + row;
-      const uint32_t b = ndoc & 1u, use = ndoc >> 1;
+      const uint32_t b = (uint32_t)i & 1u, use = (uint32_t)i >> 1;
       if (rank == 1) {
         TIMED_WAIT(w_xchg, mbar_wait(&ctl->xchg_empty[b], (use & 1u) ^ 1u));
         const uint32_t rbar = mapa(smem_u32(&ctl->xchg_full[b]), 0);
@@ -452,8 +462,8 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
         // merged position, which is computed from both loaded values (always 1: positions are non-negative).
         mbar_arrive_cluster_n(mapa(smem_u32(&ctl->xchg_empty[b]), 1), 1u + ((uint32_t)p >> 31));
         if (f < P.F) {
-          const float o = v + __ldg(P.bias + f);
-          P.pooled[doc * P.F + f] = o > 0.0f ? o : 0.0f;
+          const float ob = v + __ldg(P.bias + f);
+          P.pooled[doc * P.F + f] = ob > 0.0f ? ob : 0.0f;
           // positions Td, Td+1 of the shortened document are positions T, T+1 of the full one
           P.argmax[doc * P.F + f] = (p >= Td && p < npos) ? p + (P.T - Td) : p;
         }
@@ -466,54 +476,11 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
   }
 }
 
-// Work items of the producers: (document, tile) pairs of this CTA pair in launch order, with the document descriptors
-// fetched a whole document ahead (their loads never stall the token-id prefetch of the document's first tile).
-struct TileWalk {
-  long long wk;
-  int pt;
-  DocRef cur_d, nxt_d;
-  __device__ __forceinline__ void init(const Params& P, int cluster_id, int nclusters) {
-    wk = cluster_id;
-    pt = 0;
-    cur_d.doc = nxt_d.doc = 0; cur_d.Td = nxt_d.Td = 0; cur_d.npt = nxt_d.npt = 1; cur_d.base = nxt_d.base = 0; cur_d.len = nxt_d.len = 0;
-    if (wk < P.N) {
-      cur_d = doc_ref(P, wk);
-      if (wk + nclusters < P.N) nxt_d = doc_ref(P, wk + nclusters);
-    }
-  }
-  // the tile after the current one: (has_next, its document, its tile index)
-  __device__ __forceinline__ bool peek(const Params& P, int nclusters, const DocRef*& d, int& pt_next) const {
-    const bool wrap = pt + 1 == cur_d.npt;
-    d = wrap ? &nxt_d : &cur_d;
-    pt_next = wrap ? 0 : pt + 1;
-    return (wrap ? wk + nclusters : wk) < P.N;
-  }
-  __device__ __forceinline__ void advance(const Params& P, int nclusters) {
-    const bool wrap = pt + 1 == cur_d.npt;
-    if (wrap) {
-      wk += nclusters;
-      cur_d = nxt_d;
-      if (wk + nclusters < P.N) nxt_d = doc_ref(P, wk + nclusters);
-      pt = 0;
-    } else {
-      ++pt;
-    }
-  }
-};
-
-// token id of slab row r of tile pt of document d (slab row r <-> document position pt*256 + rank*128 - 2 + r);
-// -1 = a zero (conv padding) row.  Unchecked: callers validate when the value is consumed, a tile later.
-__device__ __forceinline__ long long slab_token(const Params& P, const DocRef& d, int pt, uint32_t rank, int r) {
-  const int pos = pt * 2 * TILE_M + (int)rank * TILE_M - 2 + r;
-  if (!(r < TILE_M + 2 && pos >= 0 && pos < d.Td)) return -1;
-  if (P.tok32 == nullptr) return __ldg(P.idx + d.doc * (long long)P.T + pos);
-  return pos < d.len ? (long long)__ldg(P.tok32 + d.base + pos) : P.pad_id;
-}
-
 // ---- TMA team: slabs 0 .. tma_slabs-1 of every tile.  Row group g (rows 4g .. 4g+3) of a slab belongs to lane
 // g / NUM_TMA_WARPS of TMA warp g % NUM_TMA_WARPS; the four table rows stay in registers for the tile's slabs.
+// Slab row r of tile t of this CTA is stream row t*256 + rank*128 + r: a lane's four tokens are one aligned 16-byte load.
 __device__ __forceinline__ void tma_role(const Params& P, const CUtensorMap* tmap, SharedCtl* ctl, uint8_t* ring, uint32_t rank,
-                                         int cluster_id, int nclusters, int pwarp, int lane) {
+                                         int cluster_id, int pwarp, int lane) {
   // row group g of a slab (rows 4g .. 4g+3): warp g % NUM_TMA_WARPS, lane (g / NUM_TMA_WARPS) % 32, the lane's j-th group
   constexpr int GPL = TMA_GROUPS_PER_LANE;
   const int warp_groups = (NGROUPS - pwarp + NUM_TMA_WARPS - 1) / NUM_TMA_WARPS;     // groups of this warp
@@ -531,35 +498,32 @@ __device__ __forceinline__ void tma_role(const Params& P, const CUtensorMap* tma
   const uint32_t leader_t0 = mapa(smem_u32(&ctl->landed_t[0]), 0);                    // both CTAs' TMA copies complete on the leader's barriers
   const int zero_row = (int)P.V;                         // row V of the shadow table is all zero (conv padding)
   const unsigned issue_mask = __activemask();
-  auto rows_of = [&](const long long (&tok)[4], int (&out)[4]) {
+  auto rows_of = [&](const int4& tok, int (&out)[4]) {
+    const int t4[4] = {tok.x, tok.y, tok.z, tok.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      if (tok[k] < -1 || tok[k] >= P.V) __trap();        // the reference device-asserts on OOB ids
-      out[k] = tok[k] < 0 ? zero_row : (int)tok[k];
+      if (t4[k] < -1 || t4[k] >= P.V) __trap();          // the reference device-asserts on OOB ids
+      out[k] = t4[k] < 0 ? zero_row : t4[k];
     }
   };
   const bool prof_on = P.prof != nullptr && cluster_id == 0;
   long long w_empty = 0, w_issue = 0, t_begin = clock64();
-  TileWalk W;
-  W.init(P, cluster_id, nclusters);
+  const int ntiles = __ldg(P.head + cluster_id).x;
+  const int4* srow = reinterpret_cast<const int4*>(P.stream + (long long)cluster_id * P.stream_stride + (long long)rank * TILE_M);
   int cur[GPL][4];
-  long long nxt[GPL][4];
+  int4 nxt[GPL];
 #pragma unroll
   for (int j = 0; j < GPL; ++j) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) nxt[j][k] = (W.wk < P.N && j < my_groups) ? slab_token(P, W.cur_d, 0, rank, 4 * grp[j] + k) : -1;
+    nxt[j] = (ntiles > 0 && j < my_groups) ? __ldg(srow + grp[j]) : make_int4(-1, -1, -1, -1);
     rows_of(nxt[j], cur[j]);
   }
   uint32_t slab = 0;                                     // running slab index of this CTA: slot = slab % nslots, use = slab / nslots
-  while (W.wk < P.N) {
-    const DocRef* nd;
-    int pt_next;
-    const bool more = W.peek(P, nclusters, nd, pt_next);
+  for (int t = 0; t < ntiles; ++t) {
+    const bool more = t + 1 < ntiles;
     if (more) {
 #pragma unroll
       for (int j = 0; j < GPL; ++j)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) nxt[j][k] = j < my_groups ? slab_token(P, *nd, pt_next, rank, 4 * grp[j] + k) : -1;
+        if (j < my_groups) nxt[j] = __ldg(srow + (long long)(t + 1) * (2 * TILE_M / 4) + grp[j]);
     }
     for (int s = 0; s < P.tma_slabs; ++s) {
       const uint32_t slot = (slab + s) % nslots, use = (slab + s) / nslots;
@@ -579,7 +543,6 @@ __device__ __forceinline__ void tma_role(const Params& P, const CUtensorMap* tma
 #pragma unroll
       for (int j = 0; j < GPL; ++j) rows_of(nxt[j], cur[j]);
     }
-    W.advance(P, nclusters);
   }
   if (prof_on && pwarp == 0 && lane == 0) {
     unsigned long long* o = P.prof + rank * 16 + 4;
@@ -593,8 +556,7 @@ __device__ __forceinline__ void tma_role(const Params& P, const CUtensorMap* tma
 // cp.async.mbarrier.arrive.noinc, which the hardware turns into an arrival once those copies have landed -- no
 // wait_group, no MEMBAR in the producer (round 1's producer stalled ~700 cycles per slab on exactly that); the
 // consumer side (MMA warp / relay) executes the generic->async proxy fence after the barrier completes.
-__device__ __forceinline__ void ldg_role(const Params& P, SharedCtl* ctl, uint8_t* ring, uint32_t rank, int cluster_id, int nclusters,
-                                         int ptid) {
+__device__ __forceinline__ void ldg_role(const Params& P, SharedCtl* ctl, uint8_t* ring, uint32_t rank, int cluster_id, int ptid) {
   const int spt = (P.Kc + CPS - 1) / CPS;
   if (P.tma_slabs >= spt) return;                        // narrow rows: the TMA team stages everything
   const int c8 = ptid & 7, r0 = ptid >> 3;
@@ -608,25 +570,23 @@ __device__ __forceinline__ void ldg_role(const Params& P, SharedCtl* ctl, uint8_
   const bool in_last = c8 < last_slab_chunks;
   const bool prof_on = P.prof != nullptr && cluster_id == 0;
   long long w_empty = 0, t_begin = clock64();
-  TileWalk W;
-  W.init(P, cluster_id, nclusters);
-  long long cur[ROWS_PER_THREAD], nxt[ROWS_PER_THREAD];
+  const int ntiles = __ldg(P.head + cluster_id).x;
+  const int* srow = P.stream + (long long)cluster_id * P.stream_stride + (long long)rank * TILE_M + r0;
+  auto tokens_of = [&](int t, int (&out)[ROWS_PER_THREAD]) {
 #pragma unroll
-  for (int k = 0; k < ROWS_PER_THREAD; ++k) cur[k] = W.wk < P.N ? slab_token(P, W.cur_d, 0, rank, r0 + LDG_ROW_STEP * k) : -1;
+    for (int k = 0; k < ROWS_PER_THREAD; ++k)
+      out[k] = (k < ROWS_PER_THREAD - 1 || last_row) ? __ldg(srow + (long long)t * (2 * TILE_M) + LDG_ROW_STEP * k) : -1;
+  };
+  int cur[ROWS_PER_THREAD], nxt[ROWS_PER_THREAD];
+  if (ntiles > 0) tokens_of(0, cur);
   uint32_t slab = 0;
-  while (W.wk < P.N) {
-    const DocRef* nd;
-    int pt_next;
-    const bool more = W.peek(P, nclusters, nd, pt_next);
-    if (more) {
-#pragma unroll
-      for (int k = 0; k < ROWS_PER_THREAD; ++k) nxt[k] = slab_token(P, *nd, pt_next, rank, r0 + LDG_ROW_STEP * k);
-    }
+  for (int t = 0; t < ntiles; ++t) {
+    if (t + 1 < ntiles) tokens_of(t + 1, nxt);
     const uint8_t* src[ROWS_PER_THREAD];
 #pragma unroll
     for (int k = 0; k < ROWS_PER_THREAD; ++k) {
       if (cur[k] < -1 || cur[k] >= P.V) __trap();        // the reference device-asserts on OOB ids
-      src[k] = cur[k] < 0 ? zero_row : thread_base + cur[k] * P.row_bytes;
+      src[k] = cur[k] < 0 ? zero_row : thread_base + (long long)cur[k] * P.row_bytes;
     }
     for (int s = P.tma_slabs; s < spt; ++s) {
       const uint32_t slot = (slab + s) % nslots, use = (slab + s) / nslots;
@@ -643,7 +603,6 @@ __device__ __forceinline__ void ldg_role(const Params& P, SharedCtl* ctl, uint8_
     slab += (uint32_t)spt;
 #pragma unroll
     for (int k = 0; k < ROWS_PER_THREAD; ++k) cur[k] = nxt[k];
-    W.advance(P, nclusters);
   }
   if (prof_on && ptid == 0) {
     unsigned long long* o = P.prof + rank * 16 + 12;
@@ -654,30 +613,24 @@ __device__ __forceinline__ void ldg_role(const Params& P, SharedCtl* ctl, uint8_
 // Rank 1's otherwise idle MMA warp: tells the leader when each cp.async slab of THIS CTA has landed (the asynchronous
 // arrivals of cp.async can only target a barrier of their own CTA; the pair's MMA is issued by rank 0).  TMA slabs need
 // no relay: their copies complete on the leader's barrier directly.
-__device__ __forceinline__ void relay_role(const Params& P, SharedCtl* ctl, int cluster_id, int nclusters) {
+__device__ __forceinline__ void relay_role(const Params& P, SharedCtl* ctl, int cluster_id) {
   const int spt = (P.Kc + CPS - 1) / CPS;
   const uint32_t leader_l0 = mapa(smem_u32(&ctl->landed_l[0]), 0);
   const uint32_t nslots = (uint32_t)P.nslots;
+  const int ntiles = __ldg(P.head + cluster_id).x;
   uint32_t slab = 0, par_l = 0u;                         // per-slot phase parity of landed_l (bit = slot)
-  for (long long k = cluster_id; k < P.N; k += nclusters) {
-    long long doc;
-    int Td;
-    work_item(P, k, doc, Td);
-    const int npt = tiles_of(Td);
-    for (int pt = 0; pt < npt; ++pt)
-      for (int s = 0; s < spt; ++s, ++slab) {
-        const uint32_t slot = slab % nslots;
-        if (s >= P.tma_slabs) {
-          mbar_wait(&ctl->landed_l[slot], (par_l >> slot) & 1u); par_l ^= 1u << slot;
-          fence_proxy_async();                            // cp.async wrote through the generic proxy, the tensor cores read through the async proxy
-          mbar_arrive_cluster(leader_l0 + slot * 8u);
-        }
+  for (int t = 0; t < ntiles; ++t)
+    for (int s = 0; s < spt; ++s, ++slab) {
+      const uint32_t slot = slab % nslots;
+      if (s >= P.tma_slabs) {
+        mbar_wait(&ctl->landed_l[slot], (par_l >> slot) & 1u); par_l ^= 1u << slot;
+        fence_proxy_async();                              // cp.async wrote through the generic proxy, the tensor cores read through the async proxy
+        mbar_arrive_cluster(leader_l0 + slot * 8u);
       }
-  }
+    }
 }
 
-__device__ __forceinline__ void mma_role(const Params& P, SharedCtl* ctl, const uint8_t* bsm, const uint8_t* ring, int cluster_id,
-                                         int nclusters, int lane) {
+__device__ __forceinline__ void mma_role(const Params& P, SharedCtl* ctl, const uint8_t* bsm, const uint8_t* ring, int cluster_id, int lane) {
   const int spt = (P.Kc + CPS - 1) / CPS;
   const uint32_t idesc = umma_idesc(P.fmt, P.Npad);
   const uint32_t a_base = smem_u32(ring), b_base = smem_u32(bsm);
@@ -697,12 +650,9 @@ __device__ __forceinline__ void mma_role(const Params& P, SharedCtl* ctl, const 
   uint32_t slot = 0, it = 0, par_t = 0u, par_l = 0u;     // par_*: per-slot phase parity of the landed barriers (bit = slot)
   const bool prof_on = P.prof != nullptr && cluster_id == 0;
   long long w_tmem = 0, w_full = 0, t_begin = clock64();
-  for (long long k = cluster_id; k < P.N; k += nclusters) {
-    long long doc;
-    int Td;
-    work_item(P, k, doc, Td);
-    const int npt = tiles_of(Td);
-    for (int pt = 0; pt < npt; ++pt, ++it) {
+  const uint32_t ntiles = (uint32_t)__ldg(P.head + cluster_id).x;
+  {
+    for (; it < ntiles; ++it) {                          // tiles of 256 consecutive windows of the pair's stream
       const uint32_t buf = it % NACC, use = it / NACC;
       TIMED_WAIT(w_tmem, mbar_wait(&ctl->tmem_empty[buf], (use & 1u) ^ 1u));       // both CTAs' epilogues drained this accumulator
       tc_fence_after();
@@ -746,7 +696,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  const int cluster_id = blockIdx.x >> 1;
   const int nh = P.Npad / 2;
   const uint32_t b_bytes = (uint32_t)(3 * P.Kc * nh * 16);
 
@@ -792,23 +742,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
 
   if (warp < NUM_EPI_WARPS) {
     switch (nh) {
-      case 8:  epilogue_role<8>(P, ctl, rank, cluster_id, nclusters, warp, lane); break;
-      case 16: epilogue_role<16>(P, ctl, rank, cluster_id, nclusters, warp, lane); break;
-      case 24: epilogue_role<24>(P, ctl, rank, cluster_id, nclusters, warp, lane); break;
-      case 32: epilogue_role<32>(P, ctl, rank, cluster_id, nclusters, warp, lane); break;
-      case 40: epilogue_role<40>(P, ctl, rank, cluster_id, nclusters, warp, lane); break;
-      case 48: epilogue_role<48>(P, ctl, rank, cluster_id, nclusters, warp, lane); break;
-      case 56: epilogue_role<56>(P, ctl, rank, cluster_id, nclusters, warp, lane); break;
-      default: epilogue_role<64>(P, ctl, rank, cluster_id, nclusters, warp, lane); break;
+      case 8:  epilogue_role<8>(P, ctl, rank, cluster_id, warp, lane); break;
+      case 16: epilogue_role<16>(P, ctl, rank, cluster_id, warp, lane); break;
+      case 24: epilogue_role<24>(P, ctl, rank, cluster_id, warp, lane); break;
+      case 32: epilogue_role<32>(P, ctl, rank, cluster_id, warp, lane); break;
+      case 40: epilogue_role<40>(P, ctl, rank, cluster_id, warp, lane); break;
+      case 48: epilogue_role<48>(P, ctl, rank, cluster_id, warp, lane); break;
+      case 56: epilogue_role<56>(P, ctl, rank, cluster_id, warp, lane); break;
+      default: epilogue_role<64>(P, ctl, rank, cluster_id, warp, lane); break;
     }
   } else if (warp < NUM_EPI_WARPS + NUM_LDG_WARPS) {
-    ldg_role(P, ctl, ring, rank, cluster_id, nclusters, threadIdx.x - NUM_EPI_WARPS * 32);
+    ldg_role(P, ctl, ring, rank, cluster_id, threadIdx.x - NUM_EPI_WARPS * 32);
   } else if (warp < MMA_WARP) {
-    tma_role(P, &tmap, ctl, ring, rank, cluster_id, nclusters, warp - NUM_EPI_WARPS - NUM_LDG_WARPS, lane);
+    tma_role(P, &tmap, ctl, ring, rank, cluster_id, warp - NUM_EPI_WARPS - NUM_LDG_WARPS, lane);
   } else if (rank == 0) {
-    mma_role(P, ctl, bsm, ring, cluster_id, nclusters, lane);
+    mma_role(P, ctl, bsm, ring, cluster_id, lane);
   } else if (lane == 0) {
-    relay_role(P, ctl, cluster_id, nclusters);
+    relay_role(P, ctl, cluster_id);
   }
 
   tc_fence_before();
@@ -818,6 +768,123 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) conv
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(ctl->tmem_base), "r"(TMEM_COLS) : "memory");
   }
+}
+
+// ---------------------------------------------------------------- window streams
+// Work item k (position in doc_order, or the document itself without a plan) -> (cluster, index inside the cluster).
+// Rounds of nc items alternate direction (0..nc-1, nc-1..0, ...): with doc_order sorted by decreasing length every
+// pair of rounds hands each cluster nearly the same number of windows.
+__device__ __forceinline__ void item_home(long long k, int nc, int& c, int& i) {
+  i = (int)(k / nc);
+  const int pos = (int)(k % nc);
+  c = (i & 1) ? nc - 1 - pos : pos;
+}
+__device__ __forceinline__ long long item_of(int c, int i, int nc) { return (long long)i * nc + ((i & 1) ? nc - 1 - c : c); }
+
+struct StreamWs {
+  int2* head;                // [nc] (tiles, documents)
+  int4* dlist;               // [nc][dlist_stride]
+  int* stream;               // [nc][stream_stride]
+  long long dlist_stride, stream_stride;
+};
+
+constexpr int PLAN_THREADS = 256;
+
+// one block per cluster: exclusive scan of (effective length + 2) over the cluster's documents -> dlist, head, and the
+// -1 rows that close the stream (two zero rows after the last document, then filler up to the last tile's halo)
+__global__ void __launch_bounds__(PLAN_THREADS) stream_plan_kernel(long long N, int T, int nc, const int* __restrict__ doc_len,
+                                                                   const int* __restrict__ doc_order, StreamWs W) {
+  __shared__ int wsum[PLAN_THREADS / 32];
+  __shared__ int carry_s;
+  const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long rounds = N / nc;
+  const int rem = (int)(N % nc);
+  const int last_pos = (rounds & 1) ? nc - 1 - c : c;
+  const int nd = (int)rounds + (last_pos < rem ? 1 : 0);
+  int4* dl = W.dlist + (long long)c * W.dlist_stride;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < nd; i0 += PLAN_THREADS) {
+    const int i = i0 + tid;
+    int doc = 0, len = 0, w = 0;
+    if (i < nd) {
+      const long long k = item_of(c, i, nc);
+      doc = doc_order ? __ldg(doc_order + k) : (int)k;
+      len = doc_len ? __ldg(doc_len + doc) : T;
+      w = len + 2;
+    }
+    int incl = w;                                       // inclusive scan inside the warp
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    int before = carry_s;
+    for (int w2 = 0; w2 < warp; ++w2) before += wsum[w2];
+    if (i < nd) dl[i] = make_int4(doc, len, before + incl - w, 0);
+    __syncthreads();
+    if (tid == PLAN_THREADS - 1) carry_s = before + incl;
+    __syncthreads();
+  }
+  const int total = carry_s;                            // windows of this cluster
+  const int ntiles = (total + 2 * TILE_M - 1) / (2 * TILE_M);
+  if (tid == 0) W.head[c] = make_int2(ntiles, nd);
+  int* st = W.stream + (long long)c * W.stream_stride;
+  for (int u = total + tid; u < ntiles * 2 * TILE_M + 4; u += PLAN_THREADS) st[u] = -1;
+}
+
+// one warp per work item: the document's two opening zero rows and its rows' token ids (validated: the reference
+// device-asserts on out-of-range ids)
+__global__ void __launch_bounds__(256) stream_fill_kernel(long long N, int T, int nc, long long V, const long long* __restrict__ idx,
+                                                          const int* __restrict__ tok32, const long long* __restrict__ off, long long pad_id,
+                                                          StreamWs W) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * 8;
+  for (long long k = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); k < N; k += warps) {
+    int c, i;
+    item_home(k, nc, c, i);
+    const int4 e = __ldg(W.dlist + (long long)c * W.dlist_stride + i);
+    int* st = W.stream + (long long)c * W.stream_stride + e.z;
+    if (lane < 2) st[lane] = -1;
+    st += 2;
+    if (idx) {
+      const long long* row = idx + (long long)e.x * T;
+      for (int p = lane; p < e.y; p += 32) {
+        const long long t = __ldg(row + p);
+        if (t < 0 || t >= V) __trap();
+        st[p] = (int)t;
+      }
+    } else {
+      const long long base = __ldg(off + e.x);
+      const int len = (int)(__ldg(off + e.x + 1) - base);
+      for (int p = lane; p < e.y; p += 32) {
+        const long long t = p < len ? (long long)__ldg(tok32 + base + p) : pad_id;
+        if (t < 0 || t >= V) __trap();
+        st[p] = (int)t;
+      }
+    }
+  }
+}
+
+// workspace carve-up for `nc` clusters (host): [head][dlist][stream], every part 16-byte aligned
+inline long long stream_ws_layout(long long N, int T, int nc, void* ws, StreamWs* out) {
+  const long long maxnd = (N + nc - 1) / nc;
+  const long long dstride = maxnd;
+  const long long sstride = ((maxnd * (T + 2) + 2 * TILE_M - 1) / (2 * TILE_M)) * (2 * TILE_M) + 8;   // whole tiles + the last tile's halo
+  const long long head_b = (((long long)nc * 8) + 15) & ~15LL;
+  const long long dl_b = (long long)nc * dstride * 16;
+  const long long st_b = (long long)nc * sstride * 4;
+  if (out) {
+    uint8_t* b = static_cast<uint8_t*>(ws);
+    out->head = reinterpret_cast<int2*>(b);
+    out->dlist = reinterpret_cast<int4*>(b + head_b);
+    out->stream = reinterpret_cast<int*>(b + head_b + dl_b);
+    out->dlist_stride = dstride;
+    out->stream_stride = sstride;
+  }
+  return head_b + dl_b + st_b;
 }
 
 // ---------------------------------------------------------------- weight packing
@@ -896,12 +963,35 @@ extern "C" int r4r_conv_pack_weights(const float* conv_w, int E, int F, void* wp
   return 0;
 }
 
+// Workspace of one r4r_conv_pool_tc launch over N documents of T rows: the work lists and window streams of its CTA pairs,
+// sized for the worst case (no padding to skip) at any cluster count the launch may use.
+extern "C" int64_t r4r_conv_stream_ws_bytes(int64_t N, int T) {
+  if (N < 0 || T <= 0) return -1;
+  if (N == 0) return 16;
+  static int pairs = 0;
+  if (pairs == 0) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    pairs = sms / 2 > 0 ? sms / 2 : 1;
+  }
+  // the byte count is not monotonic in the cluster count (per-cluster rounding): take the maximum over all of them
+  long long best = 0;
+  const int ncmax = (int)(N < pairs ? N : pairs);
+  for (int nc = 1; nc <= ncmax; ++nc) {
+    const long long b = stream_ws_layout(N, T, nc, nullptr, nullptr);
+    if (b > best) best = b;
+  }
+  return best;
+}
+
 static int conv_pool_tc_launch(const void* shadow, int64_t V, int Epad, int E, int dtype,
                                const int64_t* idx, const int32_t* tok32, const int64_t* off, int64_t pad_id, int64_t N, int T,
                                const void* wpack, const float* conv_b, int F,
                                float* pooled, int32_t* argmax,
-                               const int32_t* doc_len, const int32_t* doc_order, void* stream) {
+                               const int32_t* doc_len, const int32_t* doc_order, void* ws, void* stream) {
   R4R_REQUIRE(shadow && (idx || (tok32 && off)) && wpack && conv_b && pooled && argmax, R4R_EINVAL, "conv_pool_tc: null pointer");
+  R4R_REQUIRE(ws || N == 0, R4R_EINVAL, "conv_pool_tc: null workspace (r4r_conv_stream_ws_bytes)");
+  R4R_REQUIRE(N < (1LL << 31), R4R_EUNSUP, "conv_pool_tc: N=%lld documents exceed the work-list index range", (long long)N);
   R4R_REQUIRE(idx || (pad_id >= 0 && pad_id < V), R4R_EINVAL, "conv_pool_tc: pad id %lld outside the table", (long long)pad_id);
   R4R_REQUIRE(V > 0 && E > 0 && T > 0 && N >= 0, R4R_EINVAL, "conv_pool_tc: bad sizes");
   R4R_REQUIRE((T + 2 + 2 * TILE_M - 1) / (2 * TILE_M) <= 256, R4R_EUNSUP, "conv_pool_tc: T=%d exceeds 256 position tiles", T);
@@ -961,14 +1051,33 @@ static int conv_pool_tc_launch(const void* shadow, int64_t V, int Epad, int E, i
     R4R_REQUIRE(r == CUDA_SUCCESS, R4R_EINVAL, "conv_pool_tc: cuTensorMapEncodeTiled failed (%d) for V=%lld Epad=%d", (int)r, (long long)V, Epad);
   }
 
+  long long nclusters = sm_count / 2;
+  {
+    int want = g_clusters;                                  // r4r_conv_set_clusters: leave SM pairs free for a concurrent graph branch
+    const char* e = getenv("R4R_CONV_CLUSTERS");            // tuning override
+    if (e && atoi(e) >= 1) want = atoi(e);
+    if (want >= 1 && want < nclusters) nclusters = want;
+  }
+  if (nclusters > N) nclusters = N;
+
+  // window streams of this launch's CTA pairs (see Params): work list + row tokens, two small kernels
+  StreamWs W;
+  stream_ws_layout(N, T, (int)nclusters, ws, &W);
+  R4R_REQUIRE(W.stream_stride < (1LL << 31), R4R_EUNSUP, "conv_pool_tc: %lld rows per CTA pair exceed the window index range", W.stream_stride);
+  stream_plan_kernel<<<(unsigned)nclusters, PLAN_THREADS, 0, as_stream(stream)>>>(N, T, (int)nclusters, doc_len, doc_order, W);
+  R4R_CHECK_LAUNCH("conv_pool_tc (stream plan)");
+  {
+    long long b = (N + 7) / 8;
+    if (b > sm_count * 8) b = sm_count * 8;
+    stream_fill_kernel<<<(unsigned)b, 256, 0, as_stream(stream)>>>(N, T, (int)nclusters, V, reinterpret_cast<const long long*>(idx),
+                                                                 idx ? nullptr : tok32, reinterpret_cast<const long long*>(off), pad_id, W);
+    R4R_CHECK_LAUNCH("conv_pool_tc (stream fill)");
+  }
+
   Params P;
   P.shadow = static_cast<const uint8_t*>(shadow);
   P.row_bytes = (long long)Epad * 2;
   P.V = V;
-  P.idx = reinterpret_cast<const long long*>(idx);
-  P.tok32 = idx ? nullptr : tok32;
-  P.off = reinterpret_cast<const long long*>(off);
-  P.pad_id = pad_id;
   P.N = N; P.T = T; P.Kc = pl.Kc; P.F = F; P.Npad = pl.Npad;
   P.wpack = static_cast<const uint8_t*>(wpack);
   P.bias = conv_b; P.pooled = pooled; P.argmax = argmax;
@@ -980,18 +1089,11 @@ static int conv_pool_tc_launch(const void* shadow, int64_t V, int Epad, int E, i
     if (e && *e && atoi(e) >= 0) P.tma_slabs = atoi(e) < spt ? atoi(e) : spt;
   }
   P.prof = g_prof;
-  P.doc_len = doc_len;
-  P.doc_order = doc_order;
+  P.stream = W.stream; P.stream_stride = W.stream_stride;
+  P.dlist = W.dlist; P.dlist_stride = W.dlist_stride;
+  P.head = W.head;
 
   R4R_CUDA(cudaFuncSetAttribute(conv_pool_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  long long nclusters = sm_count / 2;
-  {
-    int want = g_clusters;                                  // r4r_conv_set_clusters: leave SM pairs free for a concurrent graph branch
-    const char* e = getenv("R4R_CONV_CLUSTERS");            // tuning override
-    if (e && atoi(e) >= 1) want = atoi(e);
-    if (want >= 1 && want < nclusters) nclusters = want;
-  }
-  if (nclusters > N) nclusters = N;
   conv_pool_tc_kernel<<<(unsigned)(2 * nclusters), NUM_THREADS, smem_bytes, as_stream(stream)>>>(P, tmap);
   R4R_CHECK_LAUNCH("conv_pool_tc");
   return 0;
@@ -1001,18 +1103,18 @@ extern "C" int r4r_conv_pool_tc(const void* shadow, int64_t V, int Epad, int E, 
                                 const int64_t* idx, int64_t N, int T,
                                 const void* wpack, const float* conv_b, int F,
                                 float* pooled, int32_t* argmax,
-                                const int32_t* doc_len, const int32_t* doc_order, void* stream) {
+                                const int32_t* doc_len, const int32_t* doc_order, void* ws, void* stream) {
   R4R_REQUIRE(idx, R4R_EINVAL, "conv_pool_tc: null pointer");
   return conv_pool_tc_launch(shadow, V, Epad, E, dtype, idx, nullptr, nullptr, 0, N, T, wpack, conv_b, F, pooled, argmax,
-                             doc_len, doc_order, stream);
+                             doc_len, doc_order, ws, stream);
 }
 
 extern "C" int r4r_conv_pool_tc_ragged(const void* shadow, int64_t V, int Epad, int E, int dtype,
                                        const int32_t* tokens, const int64_t* offsets, int64_t pad_id, int64_t N, int T,
                                        const void* wpack, const float* conv_b, int F,
                                        float* pooled, int32_t* argmax,
-                                       const int32_t* doc_len, const int32_t* doc_order, void* stream) {
+                                       const int32_t* doc_len, const int32_t* doc_order, void* ws, void* stream) {
   R4R_REQUIRE(tokens && offsets, R4R_EINVAL, "conv_pool_tc_ragged: null pointer");
   return conv_pool_tc_launch(shadow, V, Epad, E, dtype, nullptr, tokens, offsets, pad_id, N, T, wpack, conv_b, F, pooled, argmax,
-                             doc_len, doc_order, stream);
+                             doc_len, doc_order, ws, stream);
 }

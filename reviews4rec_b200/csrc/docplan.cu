@@ -15,14 +15,15 @@
 // positions >= T' back by + (T - T').  Values are bit-identical to processing all T rows because each
 // position is an independent dot product over the same operand rows.
 //
-// doc_order lists the documents by decreasing tile count so that the persistent CTA pairs, which
-// take work items k = cluster, cluster + nclusters, ... stay in step (longest-processing-time first).
+// doc_order lists the documents by decreasing length class (256 classes of (T+2)/255 windows): the conv launch deals
+// work items to its persistent CTA pairs in rounds of alternating direction, which with a sorted list gives every pair
+// nearly the same number of conv windows.
 // The sort is STABLE and free of global atomics: the same batch always yields the same work order.
 #include "common.cuh"
 
 namespace {
 constexpr int THREADS = 256;
-constexpr int NCLASS = 256;              // position tiles per document (conv_tc.cu: <= 256)
+constexpr int NCLASS = 256;              // length classes of the sort
 
 // one warp per document: scan backwards for the start of the trailing run of idx[T-1]
 __global__ void __launch_bounds__(THREADS) doc_extent_kernel(const int64_t* __restrict__ idx, int64_t N, int T,
@@ -60,28 +61,29 @@ __global__ void __launch_bounds__(THREADS) doc_extent_ragged_kernel(const int64_
   }
 }
 
-__device__ __forceinline__ int tile_class(int len, int tile, int ncls) {
-  const int c = (len + 2 + tile - 1) / tile;
-  return c < ncls ? c : ncls - 1;
+// class of a document of `len` rows: its len + 2 conv windows on a scale of 0 .. 255 (len <= T)
+__device__ __forceinline__ int len_class(int len, int T) {
+  const int c = (int)(((long long)(len + 2) * (NCLASS - 1)) / (T + 2));
+  return c < NCLASS ? c : NCLASS - 1;
 }
 
-// Stable counting sort by tile count, descending (documents of one class keep their batch order, so the
+// Stable counting sort by length class, descending (documents of one class keep their batch order, so the
 // work order -- and with it every timing-dependent interleaving of the conv kernel -- replays exactly).
 // Pass 1: class histogram of each group of THREADS consecutive documents.
-__global__ void __launch_bounds__(THREADS) doc_group_hist_kernel(const int32_t* __restrict__ doc_len, int64_t N, int tile, int ncls,
+__global__ void __launch_bounds__(THREADS) doc_group_hist_kernel(const int32_t* __restrict__ doc_len, int64_t N, int T, int ncls,
                                                                  int32_t* __restrict__ ghist) {
   __shared__ int h[NCLASS];
   h[threadIdx.x] = 0;
   __syncthreads();
   const int64_t n = (int64_t)blockIdx.x * THREADS + threadIdx.x;
-  if (n < N) atomicAdd(&h[tile_class(doc_len[n], tile, ncls)], 1);      // counts only: order-independent
+  if (n < N) atomicAdd(&h[len_class(doc_len[n], T)], 1);      // counts only: order-independent
   __syncthreads();
   if ((int)threadIdx.x < ncls) ghist[(int64_t)blockIdx.x * ncls + threadIdx.x] = h[threadIdx.x];
 }
 
 // Pass 2: slot of document n = #documents of longer classes + #documents of its class in earlier groups
 //         + #documents of its class earlier in its own group.
-__global__ void __launch_bounds__(THREADS) doc_order_kernel(const int32_t* __restrict__ doc_len, int64_t N, int tile, int ncls,
+__global__ void __launch_bounds__(THREADS) doc_order_kernel(const int32_t* __restrict__ doc_len, int64_t N, int T, int ncls,
                                                             const int32_t* __restrict__ ghist, int32_t* __restrict__ order) {
   __shared__ int total[NCLASS], before[NCLASS], base[NCLASS];
   __shared__ int wcnt[THREADS / 32][NCLASS];
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(THREADS) doc_order_kernel(const int32_t* __res
   }
   const int64_t n = (int64_t)blockIdx.x * THREADS + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = n < N ? tile_class(doc_len[n], tile, ncls) : -1;
+  const int c = n < N ? len_class(doc_len[n], T) : -1;
   const unsigned same = __match_any_sync(0xffffffffu, c);
   const int rank_in_warp = __popc(same & ((1u << lane) - 1u));
   if (c >= 0 && rank_in_warp == 0) wcnt[warp][c] = __popc(same);
@@ -118,24 +120,19 @@ __global__ void __launch_bounds__(THREADS) doc_order_kernel(const int32_t* __res
 }
 }  // namespace
 
-static int plan_classes(int T, int tile) {
-  int c = (T + 2 + tile - 1) / tile + 1;
-  return c < NCLASS ? c : NCLASS;
-}
 
 extern "C" int64_t r4r_doc_plan_ws_bytes(int64_t N, int T) {
   if (N < 0 || T <= 0) return -1;
-  return (cdiv64(N, THREADS) * plan_classes(T, 256) + 1) * (int64_t)sizeof(int32_t);
+  return (cdiv64(N, THREADS) * NCLASS + 1) * (int64_t)sizeof(int32_t);
 }
 
 static int doc_order_launch(int64_t N, int T, const int32_t* doc_len, int32_t* doc_order, void* ws, cudaStream_t s) {
-  const int tile = 256;                               // positions per CTA-pair tile of conv_pool_tc (2 * TILE_M)
-  const int ncls = plan_classes(T, tile);
+  const int ncls = NCLASS;
   const unsigned groups = (unsigned)cdiv64(N, THREADS);
   int32_t* ghist = static_cast<int32_t*>(ws);
-  doc_group_hist_kernel<<<groups, THREADS, 0, s>>>(doc_len, N, tile, ncls, ghist);
+  doc_group_hist_kernel<<<groups, THREADS, 0, s>>>(doc_len, N, T, ncls, ghist);
   R4R_CHECK_LAUNCH("doc_group_hist");
-  doc_order_kernel<<<groups, THREADS, 0, s>>>(doc_len, N, tile, ncls, ghist, doc_order);
+  doc_order_kernel<<<groups, THREADS, 0, s>>>(doc_len, N, T, ncls, ghist, doc_order);
   R4R_CHECK_LAUNCH("doc_order");
   return 0;
 }

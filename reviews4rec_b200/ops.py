@@ -327,7 +327,7 @@ def conv_pool_forward(idx: torch.Tensor, table: torch.Tensor, conv_w: torch.Tens
         wpack = torch.empty(nbytes, device=dev, dtype=torch.uint8)
         call("r4r_conv_pack_weights", _p(conv_w), E, F, _p(wpack), dt, _stream())
         doc_len = doc_order = None
-        if _doc_plan and T + 2 > _PAIR_TILE and N > 0:
+        if _doc_plan and N > 0:
             # documents padded with a repeated token are cut to their informative prefix (exact, see
             # r4r_doc_plan in include/r4r_b200.h) and issued longest first
             doc_len = torch.empty(N, device=dev, dtype=torch.int32)
@@ -337,13 +337,15 @@ def conv_pool_forward(idx: torch.Tensor, table: torch.Tensor, conv_w: torch.Tens
                 call("r4r_doc_plan", _p(idx), N, T, _p(doc_len), _p(doc_order), _p(ws), _stream())
             else:
                 call("r4r_doc_plan_ragged", _p(ragged.offsets), N, T, _p(doc_len), _p(doc_order), _p(ws), _stream())
+        # scratch for the launch's window streams (documents of each CTA pair laid end to end, see include/r4r_b200.h)
+        sws = torch.empty(_lib.lib.r4r_conv_stream_ws_bytes(N, T), device=dev, dtype=torch.uint8)
         with _ConvTimer():
             if ragged is None:
                 call("r4r_conv_pool_tc", _p(sh), V, shadow.epad, E, dt, _p(idx), N, T, _p(wpack), _p(conv_b), F,
-                     _p(pooled), _p(argmax), _p(doc_len), _p(doc_order), _stream())
+                     _p(pooled), _p(argmax), _p(doc_len), _p(doc_order), _p(sws), _stream())
             else:
                 call("r4r_conv_pool_tc_ragged", _p(sh), V, shadow.epad, E, dt, _p(ragged.tokens), _p(ragged.offsets),
-                     ragged.pad_id, N, T, _p(wpack), _p(conv_b), F, _p(pooled), _p(argmax), _p(doc_len), _p(doc_order), _stream())
+                     ragged.pad_id, N, T, _p(wpack), _p(conv_b), F, _p(pooled), _p(argmax), _p(doc_len), _p(doc_order), _p(sws), _stream())
         used = (sh, shadow.epad, V)
         if refine:
             # fp32 value of the selected window; the backward then is the fp32 gradient (used = None)

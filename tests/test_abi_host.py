@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(raw, s), "libr4r_b200.so does not export %s" % s
     assert set(syms) == set(_lib.SIGNATURES), set(syms) ^ set(_lib.SIGNATURES)
-    assert _lib.lib.r4r_abi_version() == _lib.ABI_VERSION == 4
+    assert _lib.lib.r4r_abi_version() == _lib.ABI_VERSION == 5
 
 
 def test_argument_errors_are_reported_without_a_gpu():

@@ -157,7 +157,8 @@ def _ragged_docs(seed, N, T, V):
 @pytest.mark.parametrize("N,T", [(40, 1000), (25, 600), (12, 257), (9, 300), (1000, 1000)])
 def test_doc_plan_kernel(R, N, T):
     """r4r_doc_plan: doc_len = min(T, start of the trailing run + 3); doc_order = the STABLE permutation by
-    decreasing CTA-pair tile count (documents of one class keep their batch order: no atomics, replays exactly)."""
+    decreasing length class -- 256 classes of (T+2)/255 windows (documents of one class keep their batch order: no atomics,
+    replays exactly)."""
     import ctypes
     from reviews4rec_b200 import _lib
     idx = _ragged_docs(5, N, T, 50)
@@ -177,13 +178,16 @@ def test_doc_plan_kernel(R, N, T):
     assert doc_len.cpu().tolist() == want
     o = order.cpu().tolist()
     assert sorted(o) == list(range(N))
-    tiles = [(want[n] + 2 + 255) // 256 for n in o]
-    assert tiles == sorted(tiles, reverse=True)
-    assert o == sorted(range(N), key=lambda n: -((want[n] + 2 + 255) // 256))      # python's sort is stable
+    cls = lambda n: ((want[n] + 2) * 255) // (T + 2)
+    classes = [cls(n) for n in o]
+    assert classes == sorted(classes, reverse=True)
+    assert o == sorted(range(N), key=lambda n: -cls(n))                            # python's sort is stable
 
 
 @pytest.mark.parametrize("mode", ["f16", "bf16"])
-@pytest.mark.parametrize("N,T,E,V", [(160, 1000, 300, 500), (40, 600, 64, 90), (33, 257, 32, 50)])
+@pytest.mark.parametrize("N,T,E,V", [(160, 1000, 300, 500), (40, 600, 64, 90), (33, 257, 32, 50),
+                                     # window streams: many documents per 256-window tile, partial last round of the deal
+                                     (700, 37, 24, 60), (75, 300, 40, 80), (149, 6, 16, 20), (1000, 130, 16, 40)])
 def test_conv_doc_plan_is_exact(R, O, mode, N, T, E, V):
     """Cutting documents to their informative prefix must not change a single bit of (pooled, argmax),
     and the arg-max must be the FIRST maximum like F.max_pool1d's."""
