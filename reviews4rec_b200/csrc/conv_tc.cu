@@ -33,10 +33,11 @@
 // document row is gathered exactly once.
 //
 // Warp roles per CTA (512 threads x 128 registers, 1 CTA/SM, persistent over documents):
-//   warps 0-7   epilogue : tcgen05.ld of this CTA's 128 x N accumulator (warp w: TMEM lane quarter
-//                          w&3, column half w>>2) -> running max / tile-of-max in registers across
-//                          the tiles of a document -> per document two redux.sync per column (max,
-//                          then the smallest tile<<5|lane key among its holders = FIRST maximum) +
+//   warps 0-7   epilogue : tcgen05.ld.16x256b of this CTA's 128 x N accumulator (warp w: TMEM lane quarter
+//                          w&3, column half w>>2; a thread sees four of the warp's 32 rows and a column lives in
+//                          8 lanes) -> running max / key (tile<<5|row) in registers over the windows a document
+//                          owns -> per document three xor-shuffle steps for the max and three for the smallest
+//                          key among its holders (= FIRST maximum), all values of a step issued back to back +
 //                          a four-warp shared-memory merge -> the two CTAs' partial (max, argmax)
 //                          are merged through distributed shared memory (rank 1 stores into rank 0
 //                          with st.async) -> bias, ReLU, store
@@ -57,8 +58,10 @@
 // Work plan (docplan.cu): documents end in a run of one repeated padding token; every conv window
 // inside the run repeats a value max-pooling has already seen, so document n is processed as if it had
 // doc_len[n] = min(T, run start + 3) rows and arg-max positions >= doc_len are mapped back by
-// + (T - doc_len) -- bit-identical results, ~2.5x less work on Amazon-shaped batches -- and documents
-// are issued longest first.  Ragged input (tokens + offsets instead of padded ids) takes the same path.
+// + (T - doc_len) -- bit-identical results, ~2.5x less work on Amazon-shaped batches.  The launch then deals the
+// documents (longest first, alternating direction) to its CTA pairs and lays each pair's documents end to end as one
+// WINDOW STREAM (see Params): tiles are 256 consecutive windows of the stream, not whole tiles per document
+// (2.08 -> 1.59 tiles per Amazon-shaped document).  Ragged input (tokens + offsets) takes the same path.
 #include "common.cuh"
 #include <cuda.h>
 #include <stdlib.h>
@@ -310,14 +313,40 @@ __device__ __forceinline__ uint32_t redux_min_u32(uint32_t v) {
 }
 
 
+// tcgen05.ld .16x256b: 16 TMEM lanes x 8 columns per block.  Register 4*blk + 2*j + e of lane L holds
+// (TMEM lane  base + L/4 + 8*j,  column  8*blk + 2*(L%4) + e)  -- pinned by scripts/experiments/tmem_ld_layout.cu
+// (profiles/r2_v6_tmem_ld_layout.log).  A thread therefore sees FOUR rows of its warp's 32 (two per half of 16 lanes)
+// and a column is spread over only 8 lanes: the per-document cross-lane reduction is three shuffle steps on EC/4 values
+// per thread instead of two warp-wide reductions on each of EC columns.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_16x256b_x1(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
+
 template <int EC>   // accumulator columns handled by one epilogue warp = Npad / 2
 __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, uint32_t rank, int cluster_id, int warp, int lane) {
+  constexpr int NB = EC / 8;                              // 8-column blocks of this warp's accumulator half
   const int q = warp & 3, h = warp >> 2;
   const int row = q * 32 + lane;
+  const int rsub = lane >> 2, csub = (lane & 3) * 2;      // .16x256b: this thread's rows are rsub + 8*ri, its columns 8*blk + csub + e
   const uint32_t lane_base = (uint32_t)(q * 32) << 16;
   const uint32_t leader_tmem_empty0 = mapa(smem_u32(&ctl->tmem_empty[0]), 0);
   const bool prof_on = P.prof != nullptr && cluster_id == 0;
   long long w_full = 0, w_bar = 0, w_xchg = 0, t_begin = clock64();
+  long long c_pass = 0, c_fin = 0, c_merge = 0, c_mark = 0;   // diagnostics: cycles in the tile passes / reduction / merge + exchange
   const int nd = __ldg(P.head + cluster_id).y;
   const int4* dl = P.dlist + (long long)cluster_id * P.dlist_stride;
   const int wrow0 = (int)rank * TILE_M + q * 32;          // first window of this warp inside a tile
@@ -331,14 +360,11 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
     const int npos = Td + 2;
     const int w_end = o + npos;                           // one past the document's last window
     const int t0 = o >> 8, t1 = (w_end - 1) >> 8;         // stream tiles holding its windows
-    // running maximum per filter column and the tile it came from (one byte per column, packed
-    // four to a register)
-    float best[EC];
-    uint32_t btile[EC / 4];
+    // running maximum of this thread's four rows per column it sees, and where it came from (key = tile << 5 | row)
+    float best[NB][2];
+    uint32_t bkey[NB][2];
 #pragma unroll
-    for (int c = 0; c < EC; ++c) best[c] = -INFINITY;
-#pragma unroll
-    for (int c = 0; c < EC / 4; ++c) btile[c] = 0u;
+    for (int b = 0; b < NB; ++b) { best[b][0] = best[b][1] = -INFINITY; bkey[b][0] = bkey[b][1] = 0u; }
     bool touched = false;                                 // warp-uniform: some row of this warp belongs to the document
     for (int t = t0; t <= t1; ++t) {
       const uint32_t buf = (uint32_t)t % NACC, ph = ((uint32_t)t / NACC) & 1u;
@@ -351,38 +377,43 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
       }
       const int wbase = t * 2 * TILE_M + wrow0;           // window of lane 0
       if (wbase < w_end && wbase + 32 > o) {              // warp-uniform: the tcgen05.ld below are warp-collective
+        if (prof_on) c_mark = clock64();
         touched = true;
-        const int w = wbase + lane;
-        const bool valid = w >= o && w < w_end;
-        const uint32_t taddr = ctl->tmem_base + lane_base + buf * ACC_STRIDE + h * EC;
-        uint32_t tsh[4];
+        const int wrel = wbase - o;                       // window of the warp's row 0, relative to the document's first
+        bool valid[4];
+        uint32_t kc[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tsh[k] = (uint32_t)(t - t0) << (8 * k);
+        for (int ri = 0; ri < 4; ++ri) {
+          const int r = rsub + 8 * ri;
+          valid[ri] = (unsigned)(wrel + r) < (unsigned)npos;
+          kc[ri] = ((uint32_t)(t - t0) << 5) | (uint32_t)r;
+        }
 #pragma unroll
-        for (int c0 = 0; c0 < EC; c0 += 16) {
-          uint32_t v[16];
-          if (c0 + 16 <= EC) {
-            tmem_ld16(taddr + c0, v);
-          } else {
-            uint32_t v8[8];
-            tmem_ld8(taddr + c0, v8);
+        for (int half = 0; half < 2; ++half) {            // rows in increasing order: strict > keeps the first maximum
+          const uint32_t taddr = ctl->tmem_base + lane_base + ((uint32_t)(half * 16) << 16) + buf * ACC_STRIDE + h * EC;
+          uint32_t v[NB * 4];                             // all loads of the half are in flight before the one wait
 #pragma unroll
-            for (int c = 0; c < 8; ++c) v[c] = v8[c];
-          }
-          tmem_ld_wait();
-          if (valid) {
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              if (c0 + c < EC) {
-                float x = __uint_as_float(v[c]);
-                if (x > best[c0 + c]) {
-                  best[c0 + c] = x;
-                  btile[(c0 + c) >> 2] = (btile[(c0 + c) >> 2] & ~(0xffu << (8 * (c & 3)))) | tsh[c & 3];
-                }
-              }
+          for (int b0 = 0; b0 < NB; b0 += 4) {
+            const int nb = NB - b0 < 4 ? NB - b0 : 4;
+            if (nb == 4) {
+              tmem_ld_16x256b_x4(taddr + b0 * 8, v + 4 * b0);
+            } else {
+              if (nb >= 2) tmem_ld_16x256b_x2(taddr + b0 * 8, v + 4 * b0);
+              if (nb & 1) tmem_ld_16x256b_x1(taddr + (b0 + nb - 1) * 8, v + 4 * (b0 + nb - 1));
             }
           }
+          tmem_ld_wait();
+#pragma unroll
+          for (int b = 0; b < NB; ++b)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+              for (int e2 = 0; e2 < 2; ++e2) {
+                const float x = __uint_as_float(v[4 * b + 2 * j + e2]);
+                if (valid[half * 2 + j] && x > best[b][e2]) { best[b][e2] = x; bkey[b][e2] = kc[half * 2 + j]; }
+              }
         }
+        if (prof_on) c_pass += clock64() - c_mark;
       }
       // the accumulator is released by the document that reaches the end of the tile (later documents start in later
       // tiles), or by the pair's last document
@@ -392,31 +423,51 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
         if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + buf * 8u);
       }
     }
-    // ---- per-document reduction over the warp's 32 rows: max value, smallest position on ties.
-    // Two warp-wide reductions per column (redux.sync -> CREDUX): the maximum, then the smallest
-    // key = tile << 5 | lane among the lanes that hold it (positions within one warp are ordered by
-    // tile, then lane: same CTA rank and lane quarter).  Lane c % 32 keeps column c.
-    // (Measured alternative: one redux + a shared-memory atomicMin by the holders -- 0.417 instead of 0.334 ms per launch.)
+    // ---- per-document reduction over the warp's 32 rows: max value, smallest position on ties.  A column lives in the 8
+    // lanes with the same lane % 4: three xor-shuffle steps for the maximum, three for the smallest key = tile << 5 | row
+    // among its holders (positions within one warp are ordered by tile, then row) = FIRST maximum, as F.max_pool1d.
+    // (Measured alternatives on the .32x32b layout: two redux.sync per column 0.334 ms per launch, one redux + a
+    // shared-memory atomicMin by the holders 0.417 ms.)
+    if (prof_on) c_mark = clock64();
     if (touched) {
-      float keep_v[(EC + 31) / 32];
-      uint32_t keep_k[(EC + 31) / 32];
+      // The shuffles of one step are issued back to back for all of the thread's values: shuffles keep program order, so a
+      // value-by-value formulation is one dependent chain of 6 * EC/4 shuffle latencies (measured: 4.1 k cycles per document).
+      float m[NB][2];
+      uint32_t k[NB][2];
 #pragma unroll
-      for (int c = 0; c < EC; ++c) {
-        const float m = redux_max_f32(best[c]);
-        const uint32_t tile = (btile[c >> 2] >> (8 * (c & 3))) & 0xffu;
-        const uint32_t kmin = redux_min_u32(best[c] == m ? ((tile << 5) | (uint32_t)lane) : 0xffffffffu);
-        if (lane == (c & 31)) { keep_v[c >> 5] = m; keep_k[c >> 5] = kmin; }
+      for (int b = 0; b < NB; ++b) { m[b][0] = best[b][0]; m[b][1] = best[b][1]; }
+#pragma unroll
+      for (int step = 4; step <= 16; step <<= 1) {
+        float ov[NB][2];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) { ov[b][0] = __shfl_xor_sync(0xffffffffu, m[b][0], step); ov[b][1] = __shfl_xor_sync(0xffffffffu, m[b][1], step); }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) { m[b][0] = fmaxf(m[b][0], ov[b][0]); m[b][1] = fmaxf(m[b][1], ov[b][1]); }
       }
 #pragma unroll
-      for (int i2 = 0; i2 < (EC + 31) / 32; ++i2) {
-        const int c = lane + 32 * i2;
-        if (c < EC) {
-          const float v = keep_v[i2];
-          // window -> position of the document: (t0 + tile) * 256 + rank * 128 + q * 32 + lane - o
-          ctl->red_val[warp][c] = v;
-          ctl->red_pos[warp][c] = v == -INFINITY ? 0x7fffffff
-                                                 : (t0 + (int)(keep_k[i2] >> 5)) * 2 * TILE_M + wrow0 + (int)(keep_k[i2] & 31u) - o;
-        }
+      for (int b = 0; b < NB; ++b) {
+        k[b][0] = best[b][0] == m[b][0] ? bkey[b][0] : 0xffffffffu;
+        k[b][1] = best[b][1] == m[b][1] ? bkey[b][1] : 0xffffffffu;
+      }
+#pragma unroll
+      for (int step = 4; step <= 16; step <<= 1) {
+        uint32_t ok[NB][2];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) { ok[b][0] = __shfl_xor_sync(0xffffffffu, k[b][0], step); ok[b][1] = __shfl_xor_sync(0xffffffffu, k[b][1], step); }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) { k[b][0] = min(k[b][0], ok[b][0]); k[b][1] = min(k[b][1], ok[b][1]); }
+      }
+      if (rsub == 0) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+#pragma unroll
+          for (int e2 = 0; e2 < 2; ++e2) {
+            const int c = 8 * b + csub + e2;
+            // window -> position of the document: (t0 + tile) * 256 + rank * 128 + q * 32 + row - o
+            ctl->red_val[warp][c] = m[b][e2];
+            ctl->red_pos[warp][c] = m[b][e2] == -INFINITY ? 0x7fffffff
+                                                          : (t0 + (int)(k[b][e2] >> 5)) * 2 * TILE_M + wrow0 + (int)(k[b][e2] & 31u) - o;
+          }
       }
     } else {
 #pragma unroll
@@ -425,6 +476,7 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
         if (c < EC) { ctl->red_val[warp][c] = -INFINITY; ctl->red_pos[warp][c] = 0x7fffffff; }
       }
     }
+    if (prof_on) { const long long now = clock64(); c_fin += now - c_mark; c_mark = now; }
     TIMED_WAIT(w_bar, asm volatile("bar.sync %0, 128;" :: "r"(1 + h) : "memory"));
     const bool col_thread = row < EC;
     float v = -INFINITY;
@@ -469,10 +521,12 @@ __device__ __forceinline__ void epilogue_role(const Params& P, SharedCtl* ctl, u
         }
       }
     }
+    if (prof_on) c_merge += clock64() - c_mark;
   }
   if (prof_on && warp == 0 && lane == 0) {
     unsigned long long* o = P.prof + rank * 16;
     o[0] = (unsigned long long)(clock64() - t_begin); o[1] = w_full; o[2] = w_bar; o[3] = w_xchg;
+    if (rank == 0) { P.prof[24] = c_pass; P.prof[25] = c_fin; P.prof[26] = c_merge; P.prof[27] = (unsigned long long)nd; }   // slots unused by rank 1's teams
   }
 }
 

@@ -72,3 +72,4 @@ if os.environ.get("CONV_PROF"):
         print("rank%d tma team: total %d  wait_empty %d  tma_issue %d" % (r, *v[r * 16 + 4: r * 16 + 7]))
         print("rank%d cp.async team: total %d  wait_empty %d  wait_copies+publish %d" % (r, *v[r * 16 + 12: r * 16 + 15]))
     print("mma: total %d  wait_tmem_empty %d  wait_full %d" % tuple(v[8:11]))
+    print("rank0 epilogue warp 0: tile passes %d  reduction %d  merge+exchange (incl. its waits) %d  documents %d" % tuple(v[24:28]))
