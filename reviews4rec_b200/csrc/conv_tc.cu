@@ -889,34 +889,42 @@ __global__ void __launch_bounds__(PLAN_THREADS) stream_plan_kernel(long long N, 
   for (int u = total + tid; u < ntiles * 2 * TILE_M + 4; u += PLAN_THREADS) st[u] = -1;
 }
 
-// one warp per work item: the document's two opening zero rows and its rows' token ids (validated: the reference
-// device-asserts on out-of-range ids)
-__global__ void __launch_bounds__(256) stream_fill_kernel(long long N, int T, int nc, long long V, const long long* __restrict__ idx,
-                                                          const int* __restrict__ tok32, const long long* __restrict__ off, long long pad_id,
-                                                          StreamWs W) {
-  const int lane = threadIdx.x & 31;
-  const long long warps = (long long)gridDim.x * 8;
-  for (long long k = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); k < N; k += warps) {
+// one block per work item: the document's two opening zero rows and its rows' token ids (validated: the reference
+// device-asserts on out-of-range ids).  Every thread issues its loads of a pass together (the kernel is latency-bound:
+// a warp per document with one load in flight took 22 us per 4096 documents).
+constexpr int FILL_THREADS = 128, FILL_UNROLL = 4;
+__global__ void __launch_bounds__(FILL_THREADS) stream_fill_kernel(long long N, int T, int nc, long long V, const long long* __restrict__ idx,
+                                                                   const int* __restrict__ tok32, const long long* __restrict__ off, long long pad_id,
+                                                                   StreamWs W) {
+  for (long long k = blockIdx.x; k < N; k += gridDim.x) {
     int c, i;
     item_home(k, nc, c, i);
     const int4 e = __ldg(W.dlist + (long long)c * W.dlist_stride + i);
     int* st = W.stream + (long long)c * W.stream_stride + e.z;
-    if (lane < 2) st[lane] = -1;
+    if (threadIdx.x < 2) st[threadIdx.x] = -1;
     st += 2;
-    if (idx) {
-      const long long* row = idx + (long long)e.x * T;
-      for (int p = lane; p < e.y; p += 32) {
-        const long long t = __ldg(row + p);
-        if (t < 0 || t >= V) __trap();
-        st[p] = (int)t;
+    const long long* row = idx ? idx + (long long)e.x * T : nullptr;
+    long long base = 0;
+    int len = 0;
+    if (!idx) {
+      base = __ldg(off + e.x);
+      len = (int)(__ldg(off + e.x + 1) - base);
+    }
+    for (int p0 = 0; p0 < e.y; p0 += FILL_THREADS * FILL_UNROLL) {
+      long long t[FILL_UNROLL];
+#pragma unroll
+      for (int u = 0; u < FILL_UNROLL; ++u) {
+        const int p = p0 + u * FILL_THREADS + (int)threadIdx.x;
+        t[u] = 0;
+        if (p < e.y) t[u] = idx ? __ldg(row + p) : (p < len ? (long long)__ldg(tok32 + base + p) : pad_id);
       }
-    } else {
-      const long long base = __ldg(off + e.x);
-      const int len = (int)(__ldg(off + e.x + 1) - base);
-      for (int p = lane; p < e.y; p += 32) {
-        const long long t = p < len ? (long long)__ldg(tok32 + base + p) : pad_id;
-        if (t < 0 || t >= V) __trap();
-        st[p] = (int)t;
+#pragma unroll
+      for (int u = 0; u < FILL_UNROLL; ++u) {
+        const int p = p0 + u * FILL_THREADS + (int)threadIdx.x;
+        if (p < e.y) {
+          if (t[u] < 0 || t[u] >= V) __trap();
+          st[p] = (int)t[u];
+        }
       }
     }
   }
@@ -1121,9 +1129,9 @@ static int conv_pool_tc_launch(const void* shadow, int64_t V, int Epad, int E, i
   stream_plan_kernel<<<(unsigned)nclusters, PLAN_THREADS, 0, as_stream(stream)>>>(N, T, (int)nclusters, doc_len, doc_order, W);
   R4R_CHECK_LAUNCH("conv_pool_tc (stream plan)");
   {
-    long long b = (N + 7) / 8;
-    if (b > sm_count * 8) b = sm_count * 8;
-    stream_fill_kernel<<<(unsigned)b, 256, 0, as_stream(stream)>>>(N, T, (int)nclusters, V, reinterpret_cast<const long long*>(idx),
+    long long b = N;
+    if (b > sm_count * 64) b = sm_count * 64;
+    stream_fill_kernel<<<(unsigned)b, FILL_THREADS, 0, as_stream(stream)>>>(N, T, (int)nclusters, V, reinterpret_cast<const long long*>(idx),
                                                                  idx ? nullptr : tok32, reinterpret_cast<const long long*>(off), pad_id, W);
     R4R_CHECK_LAUNCH("conv_pool_tc (stream fill)");
   }

@@ -118,6 +118,43 @@ __global__ void __launch_bounds__(THREADS) doc_order_kernel(const int32_t* __res
     order[slot] = (int32_t)n;
   }
 }
+// Both passes in one launch for batches of up to FUSED_MAX documents: every block recounts the classes of ALL documents
+// (N reads of doc_len per block, from L2) instead of reading per-group histograms written by an earlier kernel.
+constexpr int64_t FUSED_MAX = 65536;
+__global__ void __launch_bounds__(THREADS) doc_order_fused_kernel(const int32_t* __restrict__ doc_len, int64_t N, int T,
+                                                                  int32_t* __restrict__ order) {
+  __shared__ int total[NCLASS], before[NCLASS], base[NCLASS];
+  __shared__ int wcnt[THREADS / 32][NCLASS];
+  const int c0 = threadIdx.x;                         // THREADS == NCLASS: one thread per class
+  total[c0] = 0;
+  before[c0] = 0;
+  for (int w = 0; w < THREADS / 32; ++w) wcnt[w][c0] = 0;
+  __syncthreads();
+  const int64_t first = (int64_t)blockIdx.x * THREADS;          // documents before this block's group
+  for (int64_t m = threadIdx.x; m < N; m += THREADS) {
+    const int cm = len_class(__ldg(doc_len + m), T);
+    atomicAdd(&total[cm], 1);                                     // counts only: order-independent
+    if (m < first) atomicAdd(&before[cm], 1);
+  }
+  __syncthreads();
+  {
+    int b = before[c0];
+    for (int c2 = c0 + 1; c2 < NCLASS; ++c2) b += total[c2];
+    base[c0] = b;
+  }
+  const int64_t n = first + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = n < N ? len_class(doc_len[n], T) : -1;
+  const unsigned same = __match_any_sync(0xffffffffu, c);
+  const int rank_in_warp = __popc(same & ((1u << lane) - 1u));
+  if (c >= 0 && rank_in_warp == 0) wcnt[warp][c] = __popc(same);
+  __syncthreads();
+  if (c >= 0) {
+    int slot = base[c] + rank_in_warp;
+    for (int w = 0; w < warp; ++w) slot += wcnt[w][c];
+    order[slot] = (int32_t)n;
+  }
+}
 }  // namespace
 
 
@@ -129,6 +166,11 @@ extern "C" int64_t r4r_doc_plan_ws_bytes(int64_t N, int T) {
 static int doc_order_launch(int64_t N, int T, const int32_t* doc_len, int32_t* doc_order, void* ws, cudaStream_t s) {
   const int ncls = NCLASS;
   const unsigned groups = (unsigned)cdiv64(N, THREADS);
+  if (N <= FUSED_MAX) {
+    doc_order_fused_kernel<<<groups, THREADS, 0, s>>>(doc_len, N, T, doc_order);
+    R4R_CHECK_LAUNCH("doc_order_fused");
+    return 0;
+  }
   int32_t* ghist = static_cast<int32_t*>(ws);
   doc_group_hist_kernel<<<groups, THREADS, 0, s>>>(doc_len, N, T, ncls, ghist);
   R4R_CHECK_LAUNCH("doc_group_hist");
