@@ -131,10 +131,16 @@ __global__ void __launch_bounds__(THREADS) doc_order_fused_kernel(const int32_t*
   for (int w = 0; w < THREADS / 32; ++w) wcnt[w][c0] = 0;
   __syncthreads();
   const int64_t first = (int64_t)blockIdx.x * THREADS;          // documents before this block's group
-  for (int64_t m = threadIdx.x; m < N; m += THREADS) {
-    const int cm = len_class(__ldg(doc_len + m), T);
-    atomicAdd(&total[cm], 1);                                     // counts only: order-independent
-    if (m < first) atomicAdd(&before[cm], 1);
+  // counts only (order-independent); a warp adds each class it holds once -- most documents of a batch can share one
+  // class (NARRE: every full-length review), and same-address shared-memory atomics serialise lane by lane
+  for (int64_t m0 = 0; m0 < N; m0 += THREADS) {
+    const int64_t m = m0 + threadIdx.x;
+    const int cm = m < N ? len_class(__ldg(doc_len + m), T) : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, cm);
+    if (cm >= 0 && (peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0) {
+      atomicAdd(&total[cm], __popc(peers));
+      if (m0 < first) atomicAdd(&before[cm], __popc(peers));     // m0 < first <=> the whole group precedes this block's
+    }
   }
   __syncthreads();
   {
