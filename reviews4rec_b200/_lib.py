@@ -80,7 +80,7 @@ if lib.r4r_abi_version() != ABI_VERSION:
 
 # number of kernel launches issued through this binding (bench.py reports it as gpu_launches)
 launch_count = 0
-_LAUNCHES_PER_CALL = {"r4r_conv_pool_simt": 2, "r4r_linear_bwd": 2, "r4r_shard_bucket": 2, "r4r_shard_plan": 2, "r4r_doc_plan": 2, "r4r_doc_plan_ragged": 2,
+_LAUNCHES_PER_CALL = {"r4r_conv_pool_simt": 2, "r4r_linear_bwd": 2, "r4r_shard_bucket": 2, "r4r_shard_plan": 2, "r4r_doc_plan": 3, "r4r_doc_plan_ragged": 3,
                       "r4r_conv_pool_tc": 3, "r4r_conv_pool_tc_ragged": 3}
 
 
