@@ -176,9 +176,10 @@ class CapturedStep:
         from . import _lib, ops
         launches0 = _lib.launch_count
         if words is not None:
-            # the conv kernel owns every SM it runs on; leave 4 of the 74 SM pairs to the forked lookup branch and its
-            # NCCL kernels (measured at 2 x B200: 1.335 -> 1.271 ms per step; 72 and <= 66 pairs are slower)
-            _lib.lib.r4r_conv_set_clusters(int(os.environ.get("R4R_PREFETCH_CLUSTERS", "70")))
+            # the conv kernel owns every SM it runs on; leave 8 of the 74 SM pairs to the forked lookup branch and its
+            # NCCL kernels.  Measured at 2 x B200 with the window-stream conv kernel, ms per step for 60 / 63 / 66 / 68 / 70
+            # pairs: 1.098 / 1.085 / 1.066 / 1.088 / 1.096 (the faster the conv, the more of the step the branch needs)
+            _lib.lib.r4r_conv_set_clusters(int(os.environ.get("R4R_PREFETCH_CLUSTERS", "66")))
         with torch.cuda.graph(self.graph):
             if words is not None:                   # forked branch: the NEXT step's word lookup
                 cur = torch.cuda.current_stream()
