@@ -17,10 +17,12 @@ One JSON line on stdout (rank 0):
                squared-error sum are inside the timed region, every step
   eager        the drop-in path a maintainer of the reference would run: train.train(model, MSELoss, Adam, reader, hp)
                (main.train's signature, Python-driven launches, no CUDA graph)
-  value_fp32   the same step with the fp32 CUDA-core conv (`exact` mode: reference precision), a few steps
+  value_fp32   the same step with the fp32 CUDA-core conv (`exact` mode: reference precision), a few steps;
+               .refined = the fp32-refined tensor-core mode (`f16r`: tcgen05 selects the arg-max window, value + gradient fp32)
   precision    largest relative rating error of each conv mode against the fp32 oracle on a 64-rating sample
-  roofline     the dominant kernel (fused gather+conv+pool): executed FLOPs per launch / its CUDA-event duration
-               inside the timed region, against MEASURED_PEAKS.json; traffic from the committed ncu capture
+  roofline     the dominant kernel (fused gather+conv+pool, incl. the two work-list kernels of its launch): executed
+               FLOPs per launch / its CUDA-event duration inside the timed region, against MEASURED_PEAKS.json;
+               traffic from the committed ncu capture (profiles/ncu_traffic.json)
   cpu_baseline the oracle's CPU restatement of the same step on a bounded sample (N=1 only)
 """
 import argparse

@@ -232,12 +232,6 @@ __device__ __forceinline__ void umma_commit_pair(unsigned long long* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                :: "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-      : "r"(taddr) : "memory");
-}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Diagnostics: time spent inside a barrier wait is added to a counter when profiling is on.
@@ -287,31 +281,9 @@ struct Params {
 // of the stream -- a tile holds the end of one document and the start of the next -- instead of rounding every
 // document up to whole tiles (Amazon-shaped batches: 2.08 -> 1.59 tiles per document).  The epilogue takes the
 // max / arg-max per document over the window range it owns.
-__device__ __forceinline__ int tiles_of(int Td) { return (Td + 2 + 2 * TILE_M - 1) / (2 * TILE_M); }
-
 // ------------------------------------------------------------------------------------------
 // does (ov, op) beat (v, p)?  larger value, then smaller position
 __device__ __forceinline__ bool beats(float ov, int op, float v, int p) { return ov > v || (ov == v && op < p); }
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr) : "memory");
-}
-
-__device__ __forceinline__ float redux_max_f32(float v) {
-  float m;
-  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
-  return m;
-}
-__device__ __forceinline__ uint32_t redux_min_u32(uint32_t v) {
-  uint32_t m;
-  asm volatile("redux.sync.min.u32 %0, %1, 0xffffffff;" : "=r"(m) : "r"(v));
-  return m;
-}
-
 
 // tcgen05.ld .16x256b: 16 TMEM lanes x 8 columns per block.  Register 4*blk + 2*j + e of lane L holds
 // (TMEM lane  base + L/4 + 8*j,  column  8*blk + 2*(L%4) + e)  -- pinned by scripts/experiments/tmem_ld_layout.cu

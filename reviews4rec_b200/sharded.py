@@ -186,8 +186,11 @@ class P2PTransport(Transport):
         ptrs = [self.peer_ptrs[q] + self.rank * block for q in range(P)]
         K.serve_p2p(shard, rreq, P, cap, ptrs)
         self.hdl.barrier(channel=1)                      # all peers' stores into my buffer have landed
-        # valid until this rank's NEXT exchange_rows: peers only write after the channel-0 barrier of that call,
-        # i.e. after this rank's stream has finished everything queued before it (one lookup per step)
+        # A VIEW of the symmetric buffer, valid until this rank's NEXT exchange_rows: peers only write after the
+        # channel-0 barrier of that call, i.e. after this rank's stream has finished everything queued before it.
+        # Both consumers copy out at once on the same stream (ShardedWordTable._lookup places the rows into its
+        # per-step cache, _ShardedRows.forward gathers them into its output), so one buffer may carry word rows
+        # and id rows alike.
         rows = P * cap
         return self.buf[: rows * row_bytes].view(dtype).view((rows,) + tuple(row_shape))
 
