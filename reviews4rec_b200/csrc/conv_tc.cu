@@ -3,7 +3,7 @@
 // positions.  Replaces nn.Embedding + F.conv2d(pad=(2,0)) + F.relu + F.max_pool1d
 // (DeepCoNN.py:53-54, common_pytorch_models.py:26-31).
 //
-// GEMM view per document: Y[p, f] = sum_{j<3} X[p+j-2, :] . W[f, j, :]   (M = T+2 positions,
+// GEMM view per document: Y[p, f] = sum_{j<3} X[p+j-2, :] . W[f, j, :]   (M = T+2 positions = windows,
 // N = filters, K = 3*E).  The three window rows are the SAME gathered rows shifted by one position,
 // so the A operand is staged ONCE per 128-position tile and the j-th GEMM reads it through a
 // shared-memory descriptor whose start address is advanced by j rows.
@@ -22,7 +22,8 @@
 // hot head of the Zipf distribution costs nothing (uniform ids: the same 0.150 ms).  Inside this kernel that rate is
 // BELOW the ~31 B/clk the tensor cores consume, so the TMA stages only the first slabs of every tile and a cp.async team
 // writes the rest into the same swizzled layout (see the warp roles); TMA alone: 0.451 ms per 4096 documents with seven
-// issuing warps, cp.async alone: 0.413 ms, the two together: 0.371 ms.
+// issuing warps, cp.async alone: 0.413 ms, the two together: 0.371 ms (all three before the window streams and the
+// 16x256b epilogue; the shipped kernel: 0.25-0.27 ms, sweep of the TMA share in scripts/experiments/README.md).
 //
 // CTA pair.  The filter bank W (B operand, 3*E x 100 fp16 = 180 KB) must stay resident in shared
 // memory next to the A ring, which one SM cannot hold, and a single-SM MMA of N <= 64 filters is
@@ -47,8 +48,8 @@
 //   warps 12-14 TMA      : slabs 0..tma_slabs-1 of every tile (2 of 5 at E = 300): eleven lanes per warp issue the
 //                          gather4 copies (a lane's four table rows stay in registers for the tile's slabs); both CTAs'
 //                          copies complete on the LEADER's barrier (.cta_group::2); conv padding rows fetch the all-zero
-//                          row V of the shadow table.  Both teams fetch token ids one tile ahead and document
-//                          descriptors one document ahead.
+//                          row V of the shadow table.  Both teams fetch the token ids of the next tile (contiguous
+//                          int32 rows of the pair's window stream) while the current one is staged.
 //   warp  15    MMA      : allocates all 512 TMEM columns (both CTAs) = four accumulator buffers; in
 //                          the leader CTA one elected lane issues tcgen05.mma, multicast
 //                          tcgen05.commit releases ring slots ("empty") and publishes accumulators
