@@ -287,6 +287,8 @@ def run_b200(args):
     B = args.batch or MODELS[args.model][1]
     conv_mode = args.conv_mode or MODELS[args.model][2]
     hp["batch_size"] = B
+    if args.full_length:
+        hp["synthetic_full_length"] = True
     K, W = args.steps, max(args.warmup, 3)
     ops.set_conv_mode(conv_mode)
     model = build_model(hp, dev, seed=1)                   # same seed on every rank: replicas start identical
@@ -594,7 +596,7 @@ def run_b200(args):
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"f16": "f16", "bf16": "bf16", "exact": "f32"}[conv_mode],
         "data": "synthetic",
-        "config": {"workload": MODELS[args.model][3],
+        "config": {"workload": MODELS[args.model][3] + (" -- FULL-LENGTH documents (no padding; not the SURVEY 8d shape)" if args.full_length else ""),
                    "batch_per_gpu": B, "global_batch": B * world, "conv_mode": conv_mode, "dropout": hp["dropout"],
                    "arithmetic": {"f16": "conv operands f16 (private shadow of the frozen word table + packed filters), fp32 accumulation in TMEM; everything else fp32",
                                   "bf16": "conv operands bf16, fp32 accumulation in TMEM; everything else fp32",
@@ -671,6 +673,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager", action="store_true")
     ap.add_argument("--no-fp32", action="store_true")
+    ap.add_argument("--full-length", action="store_true",
+                    help="synthetic documents without padding (every document has T informative rows): the step when the exact "
+                         "padding-run shortcut has nothing to skip; NOT the SURVEY 8(d) workload")
     ap.add_argument("--docs", default="padded", choices=["ragged", "padded"],
                     help="how the reader hands documents to the model: padded int64 tensors rebuilt on the device (default) or ops.RaggedIdx")
     ap.add_argument("--table", default="sharded", choices=["sharded", "replicated"], help="word table placement for --gpus > 1")

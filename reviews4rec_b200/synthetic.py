@@ -26,9 +26,12 @@ class _Zipf:
         return (np.searchsorted(self.cdf, u, side="left") + 1).astype(np.int64)
 
 
-def _docs(rng, zipf, n, T):
-    """[n,T] int64 token ids: Zipf tokens up to a log-normal length, then id 0."""
+def _docs(rng, zipf, n, T, full_length=False):
+    """[n,T] int64 token ids: Zipf tokens up to a log-normal length, then id 0.  ``full_length``: no padding at all
+    (every document has T informative rows: the worst case for the conv kernel's padding-run shortcut)."""
     tok = zipf.draw(rng, (n, T))
+    if full_length:
+        return tok
     length = np.clip(np.exp(rng.normal(np.log(300.0), 1.0, n)), 20, T).astype(np.int64)
     tok[np.arange(T)[None, :] >= length[:, None]] = 0
     return tok
@@ -50,6 +53,9 @@ class SyntheticReader:
         T = hyper_params.get("input_length", 1000)
         R, W = hyper_params.get("narre_num_reviews", 10), hyper_params.get("narre_num_words", 200)
         zt, zu, zi = _Zipf(V - 1, 1.0), _Zipf(U, 0.8), _Zipf(I, 0.8)
+        full = bool(hyper_params.get("synthetic_full_length", False))      # bench.py --full-length (not SURVEY 8d's shape)
+        _d = _docs
+        _docs_ = lambda rng_, z_, n_, T_: _d(rng_, z_, n_, T_, full)
         self.batch_size, self.model_type = batch_size, mt
         self.batches = []
 
@@ -65,12 +71,12 @@ class SyntheticReader:
             y = rng.choice(5, size=B, p=RATING_P).astype(np.float32) + 1.0
             this = nb_u = nb_i = None
             if mt in ("deepconn", "deepconn++"):
-                ud, idoc = _docs(rng, zt, B, T), _docs(rng, zt, B, T)
+                ud, idoc = _docs_(rng, zt, B, T), _docs_(rng, zt, B, T)
             elif mt in ("transnet", "transnet++"):
-                ud, idoc, this = _docs(rng, zt, B, T), _docs(rng, zt, B, T), _docs(rng, zt, B, T)
+                ud, idoc, this = _docs_(rng, zt, B, T), _docs_(rng, zt, B, T), _docs_(rng, zt, B, T)
             elif mt == "NARRE":
-                ud = _docs(rng, zt, B * R, W).reshape(B, R, W)
-                idoc = _docs(rng, zt, B * R, W).reshape(B, R, W)
+                ud = _docs_(rng, zt, B * R, W).reshape(B, R, W)
+                idoc = _docs_(rng, zt, B * R, W).reshape(B, R, W)
                 # neighbour ids, padded with the reference's pad id U+1 / I+1 (data.py:275-276)
                 nb_u, nb_i = zu.draw(rng, (B, R)) - 1, zi.draw(rng, (B, R)) - 1
                 k = rng.integers(1, R + 1, B)
