@@ -27,6 +27,18 @@ def test_synthetic_batches_follow_the_survey_spec():
     assert torch.equal(r2.batches[0][0][3], ud)                # seeded
 
 
+def test_full_length_option_only_removes_the_padding():
+    """bench.py --full-length: the same seeded tokens, no padding tail; the default workload is untouched."""
+    from reviews4rec_b200.synthetic import SyntheticReader
+    hp = {"model_type": "deepconn", "total_users": 1000, "total_items": 100, "input_length": 1000}
+    a = SyntheticReader(hp, 64, 1, 5001, seed=7).batches[0][0][3]
+    b = SyntheticReader(dict(hp, synthetic_full_length=True), 64, 1, 5001, seed=7).batches[0][0][3]
+    assert int((b == 0).sum()) == 0 and tuple(b.shape) == tuple(a.shape)
+    assert bool((a == 0).any())
+    live = a != 0
+    assert torch.equal(a[live], b[live])                        # where the default keeps a token it is the same token
+
+
 def test_contract_figures():
     import bench
     hp = bench.model_hp("deepconn")
